@@ -1,0 +1,88 @@
+"""ctypes loader for libfishabm.so (include/fishabm.h).  Fails loudly when the CUDA library is missing:
+there is no CPU path behind this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfishabm.so")
+
+OK, E_ARG, E_CUDA, E_STATE, E_NOMEM, E_COMM = 0, -1, -2, -3, -4, -5
+MODE_CELL_FP32, MODE_BRUTE_FP64 = 0, 1
+STREAM_CHOICE, STREAM_ERROR, STREAM_RANDOMWALK, STREAM_QUALITY, STREAM_SEED, STREAM_SAMPLE, STREAM_INIT = range(7)
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("mode", C.c_int32), ("device", C.c_int32), ("replicates", C.c_int32), ("rolling", C.c_int32),
+                ("seed", C.c_uint64), ("speed_norm", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("n_global", C.c_int32), ("capacity", C.c_int32)]
+
+
+class PassStats(C.Structure):
+    _fields_ = [("focal", C.c_uint64), ("candidates", C.c_uint64), ("interacting", C.c_uint64),
+                ("rechecked", C.c_uint64)]
+
+
+# every symbol include/fishabm.h declares (tests check the library exports each of them)
+SYMBOLS = [
+    "fishabm_params_default", "fishabm_create", "fishabm_destroy", "fishabm_last_error", "fishabm_set_state",
+    "fishabm_get_state", "fishabm_initialize", "fishabm_set_quality", "fishabm_get_quality", "fishabm_sum_quality",
+    "fishabm_load_quality_csv", "fishabm_in_zone", "fishabm_zone_counts", "fishabm_social", "fishabm_get_speed",
+    "fishabm_move", "fishabm_sample", "fishabm_step", "fishabm_feed", "fishabm_run_logged", "fishabm_get_step",
+    "fishabm_set_step", "fishabm_draw", "fishabm_last_step_ms", "fishabm_last_neighbour_ms",
+    "fishabm_last_pass_stats", "fishabm_launch_count", "fishabm_enable_stats", "fishabm_averageturn",
+    "fishabm_correctangle", "fishabm_correct_coords",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  fish_abm_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, dbl = C.c_void_p, C.c_int32, C.c_uint32, C.c_double
+    L.fishabm_params_default.argtypes = [C.POINTER(Params)]
+    L.fishabm_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.fishabm_destroy.argtypes = [vp]
+    L.fishabm_destroy.restype = None
+    L.fishabm_last_error.argtypes = [vp]
+    L.fishabm_last_error.restype = C.c_char_p
+    L.fishabm_set_state.argtypes = [vp] + [vp] * 7
+    L.fishabm_get_state.argtypes = [vp] + [vp] * 7
+    L.fishabm_initialize.argtypes = [vp, dbl]
+    L.fishabm_set_quality.argtypes = [vp, vp, i32, i32, i32]
+    L.fishabm_get_quality.argtypes = [vp, i32, vp, i32, i32, i32]
+    L.fishabm_sum_quality.argtypes = [vp, vp]
+    L.fishabm_load_quality_csv.argtypes = [C.c_char_p, vp, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.fishabm_in_zone.argtypes = [vp, i32, dbl, vp]
+    L.fishabm_zone_counts.argtypes = [vp, vp]
+    L.fishabm_social.argtypes = [vp, vp, vp, vp, vp]
+    L.fishabm_get_speed.argtypes = [vp, vp]
+    L.fishabm_move.argtypes = [vp]
+    L.fishabm_sample.argtypes = [vp]
+    L.fishabm_step.argtypes = [vp, i32]
+    L.fishabm_feed.argtypes = [vp, vp, i32]
+    L.fishabm_run_logged.argtypes = [vp, i32, vp, vp, i32]
+    L.fishabm_get_step.argtypes = [vp, C.POINTER(u32)]
+    L.fishabm_set_step.argtypes = [vp, u32]
+    L.fishabm_draw.argtypes = [vp, i32, u32, u32, u32, u32, i32, i32, C.POINTER(i32)]
+    L.fishabm_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.fishabm_last_neighbour_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.fishabm_last_pass_stats.argtypes = [vp, C.POINTER(PassStats)]
+    L.fishabm_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.fishabm_enable_stats.argtypes = [vp, i32]
+    L.fishabm_averageturn.argtypes = [vp, i32, i32]
+    L.fishabm_averageturn.restype = dbl
+    L.fishabm_correctangle.argtypes = [dbl]
+    L.fishabm_correctangle.restype = dbl
+    L.fishabm_correct_coords.argtypes = [vp, i32, i32]
+    L.fishabm_correct_coords.restype = None
+    _lib = L
+    return L

@@ -1,0 +1,684 @@
+// Device kernels of the per-step agent update (single school, cell-list mode).
+//
+// Data layout (all arrays in CELL-SORTED order, rebuilt by a counting sort after every move):
+//   rec   float4 {ox, oy, cos(dir), sin(dir)}   position as offset inside the fish's own 200x200 neighbour
+//                                                cell (ulp <= 1.5e-5 at any world size) + heading unit vector
+//   cold0 float4 {dir_deg (unwrapped), speed, speed_factor, unused}
+//   cold1 int4   {lag, sample_rate, food_intake, global id}
+//   cell  int    cell index (cy*nx+cx) of the fish
+//   cell_start[ncell+1]                          exclusive scan of the per-cell counts
+// Per-pass outputs (sorted order): cnt int4 {n15, n100, n200, front}, turn float (deg), aux uint32.
+//
+// Kernels:
+//   K1 ingest_kernel / update_kernel  - write the fish's next cell and claim its rank in that cell (atomic)
+//   K2 scan_*                         - exclusive scan of the cell counts
+//   K3 scatter_kernel                 - counting-sort scatter of the three 16-byte records
+//   K4 neighbour_kernel               - fused pair loop: in_zone counts at r=15/100/200 (330 deg), front count
+//                                       (180 deg, r=200), avoidance/alignment/attraction turn sums, averageturn,
+//                                       random walk, and sample()'s feeding decision
+//   K5 update_kernel                  - sample()/feed()/move() state transition per fish
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "philox.cuh"
+
+namespace fishk {
+
+constexpr int CELL_I = 200;          // neighbour cell edge = largest radius (fish_mod.cpp:275,589)
+constexpr float CELL_F = 200.f;
+constexpr int FOOD_I = 20;           // Structure.res_factor, fish_mod.cpp:56
+constexpr int FOOD_PER_CELL = CELL_I / FOOD_I;  // 10 food cells per neighbour-cell edge
+
+constexpr int STREAM_CHOICE = 0, STREAM_ERROR = 1, STREAM_RANDOMWALK = 2, STREAM_SAMPLE = 5, STREAM_INIT = 6;
+
+// ---- neighbour kernel configuration
+constexpr int NB_WARPS = 8;              // warps (= focal cells) per CTA
+constexpr int NB_THREADS = NB_WARPS * 32;
+constexpr int NB_CAP = 256;              // candidate records staged per warp batch
+
+constexpr float PI_F = 3.14159265358979f;
+constexpr float COS165_F = -0.96592582628906829f;   // cos(165 deg): the 330 deg field of view (fov/2, fish_mod.cpp:254)
+constexpr float BAND_R = 2.0e-4f;        // |d - r| below this -> fp64 re-check
+constexpr int FIX_SHIFT = 20;            // fixed-point fraction bits of the cos/sin accumulators
+constexpr float FIX_MAGIC = 12.0f;       // x + 12.0f has ulp 2^-20 for x in [-1,1]
+constexpr int FIX_MAGIC_BITS = 0x41400000;
+
+struct NeighArgs {
+    const float4* rec;
+    const float4* cold0;
+    const int4* cold1;
+    const int* cell_start;
+    int4* cnt;
+    float* turn;
+    uint32_t* aux;
+    unsigned long long* stats;   // [4] focal, candidates, interacting, rechecked (may be null)
+    int ncell, nx, ny;
+    int active_lag_max;          // fish with lag > this are skipped (their outputs are not needed); <0: all fish
+    int do_sample;               // evaluate sample()'s feeding decision into aux
+    uint32_t step_sample, step_move;
+    uint64_t seed;
+    uint32_t replicate;
+};
+
+// aux bits
+constexpr uint32_t AUX_WANTS = 1u;            // fish decided to feed (fish_mod.cpp:547)
+constexpr uint32_t AUX_FOOD_SHIFT = 1;        // bits 1..7: food cell index inside the neighbour cell (0..99)
+constexpr uint32_t AUX_FOOD_MASK = 0x7Fu;
+constexpr uint32_t AUX_RANDOMWALK = 1u << 8;  // turn came from the random-walk stream (fish_mod.cpp:372-374)
+constexpr uint32_t AUX_TIE_SHIFT = 9;         // tie-break draws consumed (saturating 7 bits)
+constexpr uint32_t AUX_EVALUATED = 1u << 16;  // the fish was active in this pass
+
+// atan2 in radians, result in (-pi, pi]; max abs error ~1.5e-7 rad.  (0,0) -> 0.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = __fdividef(mn, fmaxf(mx, 1e-37f));
+    const float s = t * t;
+    float p = -4.054543159e-03f;
+    p = fmaf(p, s, 2.186286711e-02f);
+    p = fmaf(p, s, -5.591218983e-02f);
+    p = fmaf(p, s, 9.642186820e-02f);
+    p = fmaf(p, s, -1.390862525e-01f);
+    p = fmaf(p, s, 1.994656476e-01f);
+    p = fmaf(p, s, -3.332986071e-01f);
+    p = fmaf(p, s, 9.999993356e-01f);
+    float r = p * t;
+    r = (ay > ax) ? (0.5f * PI_F - r) : r;
+    r = (x < 0.f) ? (PI_F - r) : r;
+    return copysignf(r, y);
+}
+
+// Literal fp64 restatement of the per-pair predicates of in_zone (fish_mod.cpp:237-254) for a pair whose fp32
+// evaluation fell inside a rounding band.  dx,dy are exact (offsets are fp32, cell shifts are multiples of 200).
+// Products and sums are kept unfused so the operation order is the reference's.
+// bit0 dist<15, bit1 dist<100, bit2 dist<200, bit3 angle<165, bit4 angle<90
+__device__ __noinline__ unsigned exact_pair_bits(float oxi, float oyi, float dir_deg, float oxj, float oyj, int kcode) {
+    const double sx = (double)((kcode % 3) - 1) * 200.0, sy = (double)((kcode / 3) - 1) * 200.0;
+    const double x = __dadd_rn(__dsub_rn((double)oxj, (double)oxi), sx);
+    const double y = __dadd_rn(__dsub_rn((double)oyj, (double)oyi), sy);
+    const double ang = __ddiv_rn(__dmul_rn((double)dir_deg, M_PI), 180.0);
+    const double c = cos(ang), s = sin(ang);
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+    const double q = __ddiv_rn(__dadd_rn(__dmul_rn(c, x), __dmul_rn(s, y)), dist);
+    const double angle = __ddiv_rn(__dmul_rn(acos(q), 180.0), M_PI);
+    unsigned b = 0;
+    if (dist < 15.0) b |= 1u;
+    if (dist < 100.0) b |= 2u;
+    if (dist < 200.0) b |= 4u;
+    if (angle < 165.0) b |= 8u;
+    if (angle < 90.0) b |= 16u;
+    return b;
+}
+
+// getangle's wrap applied to the standard representative beta (rad) for a focal fish whose raw heading is
+// outside (-540, 540): world bearing A in [0,360), minus the raw heading, ONE correctangle, fold > 180
+// (fish_mod.cpp:440-459).  Everywhere else the result equals beta, which the fast path returns directly.
+__device__ __noinline__ float getangle_wrap_exotic(float beta_rad, float dir_raw_deg) {
+    const double b = (double)beta_rad * (180.0 / M_PI);
+    double dm = fmod((double)dir_raw_deg, 360.0);
+    if (dm < 0) dm += 360.0;
+    double A = b + dm;
+    if (A < 0) A += 360.0; else if (A >= 360.0) A -= 360.0;
+    double a = A - (double)dir_raw_deg;
+    if (a < 0) a += 360.0; else if (a >= 360.0) a -= 360.0;
+    if (a > 180.0) a -= 360.0;
+    return (float)(a * (M_PI / 180.0));
+}
+
+struct FocalAcc {
+    int n15, n100, n200, nf;        // running counts
+    int ax0, ay0, ax1, ay1, ax2, ay2;  // fixed-point cos/sin sums of the current batch (avoid, align, attract)
+    double sx0, sy0, sx1, sy1, sx2, sy2;  // folded sums (exact integers)
+    int ties;
+    unsigned cand, inter, rechk;
+};
+
+__device__ __forceinline__ void fold_batch(FocalAcc& A) {
+    A.sx0 += (double)A.ax0; A.sy0 += (double)A.ay0;
+    A.sx1 += (double)A.ax1; A.sy1 += (double)A.ay1;
+    A.sx2 += (double)A.ax2; A.sy2 += (double)A.ay2;
+    A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0;
+}
+
+// averageturn (fish_mod.cpp:379-408) from the cos/sin sums; degrees
+__device__ __forceinline__ double average_from_sums(double x, double y) {
+    if (y == 0.0) return (x >= 0.0) ? 0.0 : 180.0;
+    return atan2(y, x) * (180.0 / M_PI);
+}
+
+template <bool STATS>
+__device__ __forceinline__ void process_batch(const float4* __restrict__ tile, const uint32_t* __restrict__ tj, int fill,
+                                              bool active, float fx, float fy, float fc, float fs, float dir_raw,
+                                              bool exotic, uint32_t my_id, const NeighArgs& a, FocalAcc& A) {
+    if (!active) return;
+    for (int k = 0; k < fill; ++k) {
+        const float4 q = tile[k];  // same address in every lane: shared-memory broadcast
+        const float dx = q.x - fx, dy = q.y - fy;
+        const float d2 = fmaf(dx, dx, dy * dy);
+        if (STATS) A.cand++;
+        // d2 == 0: the fish itself or a coincident fish; the reference's acos(0/0) is NaN and the pair is
+        // dropped from every count (fish_mod.cpp:252-254)
+        if (!(d2 < (CELL_F + BAND_R) * (CELL_F + BAND_R)) || d2 == 0.f) continue;
+        const float rinv = rsqrtf(d2);
+        const float d = d2 * rinv;
+        const float dot = fmaf(fc, dx, fs * dy);
+        const float ca = dot * rinv;  // cos of the bearing of j seen from i
+        // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
+        const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
+        bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
+        unc = unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb || fabsf(ca) > 1.f - 1.0e-6f;
+        bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
+        if (unc) {
+            const uint32_t code = tj[k];
+            const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
+            const float4 me = make_float4(fx, fy, 0.f, 0.f);
+            const unsigned b = exact_pair_bits(me.x, me.y, dir_raw, raw.x, raw.y, (int)(code >> 28));
+            in15 = b & 1u; in100 = b & 2u; in200 = b & 4u; vis = b & 8u; front = b & 16u;
+            if (STATS) A.rechk++;
+        }
+        A.nf += (front && in200) ? 1 : 0;
+        if (!(vis && in200)) continue;
+        A.n200++;
+        A.n100 += in100 ? 1 : 0;
+        A.n15 += in15 ? 1 : 0;
+        if (STATS) A.inter++;
+        // ---- turn contribution of this neighbour (fish_mod.cpp:316-351), radians
+        const bool al = in100 && !in15;
+        const float cross = fmaf(fc, dy, -fs * dx);
+        const float crossA = fmaf(fc, q.w, -fs * q.z);
+        const float dotA = fmaf(fc, q.z, fs * q.w);
+        float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
+        if (exotic) beta = getangle_wrap_exotic(beta, dir_raw);
+        float t = beta;
+        if (in15) {
+            t = beta - copysignf(PI_F, beta);
+            if (beta == 0.f) {  // neighbour dead ahead: +-180 at random (fish_mod.cpp:327-329); keyed by the neighbour's id
+                const uint32_t nid = (uint32_t)a.cold1[tj[k] & 0x0FFFFFFFu].w;
+                t = (fishrng::draw(a.seed, a.replicate, a.step_move, my_id, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
+                A.ties++;
+            }
+        } else if (al && fabsf(beta) >= PI_F) {  // exactly opposite heading: +-180 at random (fish_mod.cpp:460-462)
+            const uint32_t nid = (uint32_t)a.cold1[tj[k] & 0x0FFFFFFFu].w;
+            t = (fishrng::draw(a.seed, a.replicate, a.step_move, my_id, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
+            A.ties++;
+        }
+        const float e = d - (in15 ? 0.f : (al ? 15.f : 200.f));
+        const float kz = in15 ? 0.1f : 0.004f;
+        const float wgt = __fdividef(1.f, fmaf(kz * e, e, 2.f));
+        const float th = t * wgt;
+        float sn, cs;
+        __sincosf(th, &sn, &cs);
+        const int vx = __float_as_int(cs + FIX_MAGIC) - FIX_MAGIC_BITS;
+        const int vy = __float_as_int(sn + FIX_MAGIC) - FIX_MAGIC_BITS;
+        if (in15) { A.ax0 += vx; A.ay0 += vy; }
+        else if (al) { A.ax1 += vx; A.ay1 += vy; }
+        else { A.ax2 += vx; A.ay2 += vy; }
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a) {
+    __shared__ float4 s_tile[NB_WARPS * NB_CAP];
+    __shared__ uint32_t s_tj[NB_WARPS * NB_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int c = blockIdx.x * NB_WARPS + warp;
+    if (c >= a.ncell) return;
+    const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
+    if (s0 == e0) return;
+    const int cx = c % a.nx, cy = c / a.nx;
+    int nb_s = 0, nb_e = 0;
+    if (lane < 9) {
+        int xx = cx + (lane % 3) - 1, yy = cy + (lane / 3) - 1;
+        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
+        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
+        const int cc = yy * a.nx + xx;
+        nb_s = a.cell_start[cc];
+        nb_e = a.cell_start[cc + 1];
+    }
+    float4* tile = s_tile + warp * NB_CAP;
+    uint32_t* tj = s_tj + warp * NB_CAP;
+
+    for (int base = s0; base < e0; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < e0;
+        float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
+        int4 c1 = make_int4(0, 0, 0, 0);
+        float dir_raw = 0.f;
+        if (valid) { me = a.rec[i]; c1 = a.cold1[i]; dir_raw = a.cold0[i].x; }
+        const bool active = valid && (a.active_lag_max < 0 || c1.x <= a.active_lag_max);
+        if (!__any_sync(FULL, active)) {
+            if (valid) a.aux[i] = 0u;
+            continue;
+        }
+        const bool exotic = fabsf(dir_raw) >= 540.f;
+        FocalAcc A;
+        A.n15 = A.n100 = A.n200 = A.nf = 0;
+        A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0;
+        A.sx0 = A.sy0 = A.sx1 = A.sy1 = A.sx2 = A.sy2 = 0.0;
+        A.ties = 0; A.cand = A.inter = A.rechk = 0;
+
+        int fill = 0;
+        for (int k = 0; k < 9; ++k) {
+            const int ks = __shfl_sync(FULL, nb_s, k), ke = __shfl_sync(FULL, nb_e, k);
+            const float sx = (float)((k % 3) - 1) * CELL_F, sy = (float)((k / 3) - 1) * CELL_F;
+            for (int b = ks; b < ke;) {
+                const int m = min(ke - b, NB_CAP - fill);
+                for (int t = lane; t < m; t += 32) {
+                    float4 r = __ldg(&a.rec[b + t]);
+                    r.x += sx; r.y += sy;
+                    tile[fill + t] = r;
+                    tj[fill + t] = (uint32_t)(b + t) | ((uint32_t)k << 28);
+                }
+                fill += m; b += m;
+                if (fill == NB_CAP) {
+                    __syncwarp();
+                    process_batch<STATS>(tile, tj, fill, active, me.x, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
+                    fold_batch(A);
+                    __syncwarp();
+                    fill = 0;
+                }
+            }
+        }
+        __syncwarp();
+        process_batch<STATS>(tile, tj, fill, active, me.x, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
+        fold_batch(A);
+        __syncwarp();
+
+        if (STATS) {
+            unsigned f = __reduce_add_sync(FULL, active ? 1u : 0u);
+            unsigned cd = __reduce_add_sync(FULL, A.cand), it = __reduce_add_sync(FULL, A.inter), rc = __reduce_add_sync(FULL, A.rechk);
+            if (lane == 0 && a.stats) {
+                atomicAdd(&a.stats[0], (unsigned long long)f); atomicAdd(&a.stats[1], (unsigned long long)cd);
+                atomicAdd(&a.stats[2], (unsigned long long)it); atomicAdd(&a.stats[3], (unsigned long long)rc);
+            }
+        }
+        if (!valid) continue;
+        if (!active) { a.aux[i] = 0u; continue; }
+
+        // ---- social()'s selection (fish_mod.cpp:355-376) and averageturn (:379-408)
+        uint32_t aux = AUX_EVALUATED;
+        const int n_av = A.n15, n_al = A.n100 - A.n15, n_at = A.n200 - A.n100;
+        double turn;
+        if (n_av > 0) turn = average_from_sums(A.sx0, A.sy0);
+        else if (n_al > 0 && n_at > 0) {
+            const double aa = average_from_sums(A.sx1, A.sy1) * (M_PI / 180.0);
+            const double tt = average_from_sums(A.sx2, A.sy2) * (M_PI / 180.0);
+            double sa, ca, st, ct;
+            sincos(aa, &sa, &ca);
+            sincos(tt, &st, &ct);
+            turn = average_from_sums(1.7 * ca + 0.7 * ct, 1.7 * sa + 0.7 * st);
+        } else if (n_al > 0) turn = average_from_sums(A.sx1, A.sy1);
+        else if (n_at > 0) turn = average_from_sums(A.sx2, A.sy2);
+        else {
+            turn = (double)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_RANDOMWALK, 0, -45, 45);
+            aux |= AUX_RANDOMWALK;
+        }
+        aux |= (uint32_t)min(A.ties, 127) << AUX_TIE_SHIFT;
+
+        // ---- sample()'s decision (fish_mod.cpp:543-547); the draw is only consumed when lag == 0
+        if (a.do_sample && c1.x == 0) {
+            const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)c1.w, STREAM_SAMPLE, 0, 0, 35);
+            const bool alone = (n_av == 0 && n_al < 5);
+            if (c1.y > dr && !alone) {
+                const int fxl = min((int)me.x / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)me.y / FOOD_I, FOOD_PER_CELL - 1);
+                aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
+            }
+        }
+        a.cnt[i] = make_int4(A.n15, A.n100, A.n200, A.nf);
+        a.turn[i] = (float)turn;
+        a.aux[i] = aux;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K5: per-fish state transition
+// ------------------------------------------------------------------------------------------------------
+struct UpdateArgs {
+    float4* rec;
+    float4* cold0;
+    int4* cold1;
+    int* cell;          // current cell of the fish (sorted order)
+    const int* cell_start;
+    const int4* cnt;
+    const float* turn;
+    const uint32_t* aux;
+    int* next_cell;     // out: cell after the move
+    int* next_rank;     // out: rank claimed in that cell
+    int* next_count;    // per-cell counters being built for the next sort (atomic)
+    uint8_t* quality;   // food grid, rows x cols
+    int* upd_count;     // deferred food-grid updates (applied after this kernel)
+    int* upd_idx;
+    uint8_t* upd_val;
+    int n, nx, ny, qcols;
+    int do_sample, do_move, rolling;
+    uint32_t step_move;
+    uint64_t seed;
+    uint32_t replicate;
+    double speed_norm;
+};
+
+__global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float4 c0 = a.cold0[i];
+    int4 c1 = a.cold1[i];
+    const int mycell = a.cell[i];
+    const uint32_t aux = a.do_sample ? a.aux[i] : 0u;
+
+    if (a.do_sample) {  // sample(), fish_mod.cpp:546-556
+        if (aux & AUX_WANTS) {
+            c1.x = 10;
+            // feed(), fish_mod.cpp:560-574.  Fish that feed on the same food cell in the same step are served in
+            // id order (the reference's loop order, :541): rank = feeders of this food cell with a lower id.
+            const uint32_t key = aux & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS);
+            const int s = a.cell_start[mycell], e = a.cell_start[mycell + 1];
+            int rank = 0, total = 0;
+            for (int j = s; j < e; ++j) {
+                const uint32_t aj = a.aux[j];
+                if ((aj & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS)) == key) {
+                    total++;
+                    rank += (a.cold1[j].w < c1.w) ? 1 : 0;
+                }
+            }
+            const int fl = (int)((aux >> AUX_FOOD_SHIFT) & AUX_FOOD_MASK);
+            const int gx = (mycell % a.nx) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
+            const int gy = (mycell / a.nx) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
+            const int qi = gy * a.qcols + gx;
+            const int q = (int)a.quality[qi];
+            if (rank < q) { c0.z = 0.5f; c1.z += 1; c1.y = 30; }
+            else c1.y = 0;
+            if (rank == 0 && q > 0) {  // the grid itself is only written after every feeder has read it
+                const int k = atomicAdd(a.upd_count, 1);
+                a.upd_idx[k] = qi;
+                a.upd_val[k] = (uint8_t)(q - min(q, total));
+            }
+        } else if (c1.x == 0) c1.y += 1;
+        else c1.x -= 1;
+    }
+
+    int newcell = mycell;
+    if (a.do_move) {  // move(), fish_mod.cpp:165-179
+        const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -10, 10);
+        float4 r = a.rec[i];
+        double dir = (double)c0.x;
+        if (c1.x == 0) {
+            double d0 = dir;
+            if (d0 < 0) d0 += 360.0; else if (d0 >= 360.0) d0 -= 360.0;  // correctangle, :410-418
+            dir = d0 + ((double)a.turn[i] + (double)err);
+            double sn, cs;
+            sincospi(dir / 180.0, &sn, &cs);
+            const double stepl = (double)c0.y * (double)c0.z;  // speed * OLD speed_factor (:171-172)
+            double px = (double)r.x + stepl * cs, py = (double)r.y + stepl * sn;
+            if (a.rolling) c0.z = (float)(1.0 + 2.0 * (double)a.cnt[i].w / a.speed_norm);  // get_speed, :588-591
+            // periodic wrap (correct_coords, :466-480) in cell/offset form
+            int cx = mycell % a.nx, cy = mycell / a.nx;
+            const double kx = floor(px / (double)CELL_I), ky = floor(py / (double)CELL_I);
+            float ox = (float)(px - kx * CELL_I), oy = (float)(py - ky * CELL_I);
+            cx += (int)kx; cy += (int)ky;
+            if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
+            if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
+            cx %= a.nx; if (cx < 0) cx += a.nx;
+            cy %= a.ny; if (cy < 0) cy += a.ny;
+            newcell = cy * a.nx + cx;
+            r.x = ox; r.y = oy;
+        } else {
+            dir = dir + (double)err;  // :177-179
+        }
+        c0.x = (float)dir;
+        double sn, cs;
+        sincospi((double)c0.x / 180.0, &sn, &cs);
+        r.z = (float)cs; r.w = (float)sn;
+        a.rec[i] = r;
+        a.next_cell[i] = newcell;
+        a.next_rank[i] = atomicAdd(&a.next_count[newcell], 1);
+    }
+    a.cold0[i] = c0;
+    a.cold1[i] = c1;
+}
+
+__global__ void apply_quality_updates_kernel(uint8_t* quality, int* upd_count, const int* upd_idx, const uint8_t* upd_val) {
+    const int n = *upd_count;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) quality[upd_idx[k]] = upd_val[k];
+}
+__global__ void reset_counter_kernel(int* p) { *p = 0; }
+
+// ------------------------------------------------------------------------------------------------------
+// K1 (ingest), K2 (scan), K3 (scatter)
+// ------------------------------------------------------------------------------------------------------
+struct IngestArgs {
+    const double* coords; const double* dir; const double* speed; const double* sf;
+    const int* lag; const int* rate; const int* intake;
+    float4* rec; float4* cold0; int4* cold1;
+    int* next_cell; int* next_rank; int* next_count;
+    int n, nx, ny, id_base;
+    int* bad;  // set to 1 if a coordinate is outside [0,W] x [0,H] or not finite
+    double w, h;
+};
+
+__global__ void ingest_kernel(const IngestArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double x = a.coords[2 * (size_t)i], y = a.coords[2 * (size_t)i + 1];
+    if (!(x >= 0.0 && x <= a.w && y >= 0.0 && y <= a.h)) { *a.bad = 1; x = 0; y = 0; }
+    if (x >= a.w) x -= a.w;  // x == W is kept by the reference's strict compare (fish_mod.cpp:468); here it wraps
+    if (y >= a.h) y -= a.h;
+    int cx = (int)floor(x / CELL_I), cy = (int)floor(y / CELL_I);
+    float ox = (float)(x - (double)cx * CELL_I), oy = (float)(y - (double)cy * CELL_I);
+    if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
+    if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
+    if (cx >= a.nx) cx -= a.nx;
+    if (cy >= a.ny) cy -= a.ny;
+    const float dirf = (float)a.dir[i];
+    double sn, cs;
+    sincospi((double)dirf / 180.0, &sn, &cs);
+    a.rec[i] = make_float4(ox, oy, (float)cs, (float)sn);
+    a.cold0[i] = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
+    a.cold1[i] = make_int4(a.lag[i], a.rate[i], a.intake[i], a.id_base + i);
+    const int c = cy * a.nx + cx;
+    a.next_cell[i] = c;
+    a.next_rank[i] = atomicAdd(&a.next_count[c], 1);
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* s_warp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+        int xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, xi, o); if (lane >= o) xi += t; }
+        s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    const int res = inc - v + s_warp[w];
+    *total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+// pass 1: per-tile sums
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const int* __restrict__ count, int n, int* __restrict__ tile_sums) {
+    __shared__ int s_warp[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) v += count[base + k];
+    int total;
+    block_exclusive_scan(v, &total, s_warp);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// pass 2: exclusive scan of the tile sums (single block, any length)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets_kernel(int* tile_sums, int ntiles) {
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int b = 0; b < ntiles; b += SCAN_THREADS) {
+        const int i = b + threadIdx.x;
+        const int v = i < ntiles ? tile_sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total, s_warp);
+        if (i < ntiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+// pass 3: final exclusive scan; clears the counters for the next build; writes start[n] = total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(int* __restrict__ count, int n, const int* __restrict__ tile_sums,
+                                                                   int* __restrict__ start) {
+    __shared__ int s_warp[33];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int vals[SCAN_ITEMS];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { vals[k] = (base + k < n) ? count[base + k] : 0; v += vals[k]; }
+    int total;
+    int run = block_exclusive_scan(v, &total, s_warp) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) { start[base + k] = run; run += vals[k]; count[base + k] = 0; }
+    if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) start[n] = run;
+}
+
+struct ScatterArgs {
+    const float4* rec_in; const float4* cold0_in; const int4* cold1_in;
+    float4* rec_out; float4* cold0_out; int4* cold1_out; int* cell_out;
+    const int* next_cell; const int* next_rank; const int* start;
+    int n;
+};
+__global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int c = a.next_cell[i];
+    const int dst = a.start[c] + a.next_rank[i];
+    a.rec_out[dst] = a.rec_in[i];
+    a.cold0_out[dst] = a.cold0_in[i];
+    a.cold1_out[dst] = a.cold1_in[i];
+    a.cell_out[dst] = c;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// export / generic queries
+// ------------------------------------------------------------------------------------------------------
+struct ExportArgs {
+    const float4* rec; const float4* cold0; const int4* cold1; const int* cell;
+    double* coords; double* dir; double* speed; double* sf; int* lag; int* rate; int* intake;
+    int n, nx, id_base;
+};
+__global__ void export_kernel(const ExportArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 r = a.rec[i], c0 = a.cold0[i];
+    const int4 c1 = a.cold1[i];
+    const int c = a.cell[i];
+    const size_t id = (size_t)(c1.w - a.id_base);
+    if (a.coords) {
+        a.coords[2 * id] = (double)(c % a.nx) * CELL_I + (double)r.x;
+        a.coords[2 * id + 1] = (double)(c / a.nx) * CELL_I + (double)r.y;
+    }
+    if (a.dir) a.dir[id] = (double)c0.x;
+    if (a.speed) a.speed[id] = (double)c0.y;
+    if (a.sf) a.sf[id] = (double)c0.z;
+    if (a.lag) a.lag[id] = c1.x;
+    if (a.rate) a.rate[id] = c1.y;
+    if (a.intake) a.intake[id] = c1.z;
+}
+
+// per-pass outputs from sorted order to id order
+struct ExportPassArgs {
+    const int4* cold1; const int4* cnt; const float* turn; const uint32_t* aux;
+    int* cnt4; double* turn_out; int* n_avoid; int* n_align; int* n_attract; double* speed_out;
+    int n, id_base; double speed_norm;
+};
+__global__ void export_pass_kernel(const ExportPassArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const size_t id = (size_t)(a.cold1[i].w - a.id_base);
+    const int4 c = a.cnt[i];
+    if (a.cnt4) { a.cnt4[4 * id] = c.x; a.cnt4[4 * id + 1] = c.y; a.cnt4[4 * id + 2] = c.z; a.cnt4[4 * id + 3] = c.w; }
+    if (a.turn_out) a.turn_out[id] = (double)a.turn[i];
+    if (a.n_avoid) a.n_avoid[id] = c.x;
+    if (a.n_align) a.n_align[id] = c.y - c.x;
+    if (a.n_attract) a.n_attract[id] = c.z - c.y;
+    if (a.speed_out) a.speed_out[id] = 1.0 + 2.0 * (double)c.w / a.speed_norm;
+}
+
+// in_zone(inds,id,fov,r) for arbitrary fov / r <= 200: literal fp64 predicate over the 3x3 stencil
+struct ZoneArgs {
+    const float4* rec; const float4* cold0; const int4* cold1; const int* cell; const int* cell_start;
+    int* out; int n, nx, ny, id_base, fov_half; double r;
+};
+__global__ void in_zone_generic_kernel(const ZoneArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 me = a.rec[i];
+    const int c = a.cell[i], cx = c % a.nx, cy = c / a.nx;
+    const double ang = __ddiv_rn(__dmul_rn((double)a.cold0[i].x, M_PI), 180.0);
+    const double cs = cos(ang), sn = sin(ang);
+    int count = 0;
+    for (int k = 0; k < 9; ++k) {
+        int xx = cx + (k % 3) - 1, yy = cy + (k / 3) - 1;
+        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
+        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
+        const int cc = yy * a.nx + xx;
+        const double sx = (double)((k % 3) - 1) * 200.0, sy = (double)((k / 3) - 1) * 200.0;
+        for (int j = a.cell_start[cc]; j < a.cell_start[cc + 1]; ++j) {
+            if (j == i) continue;
+            const float4 o = a.rec[j];
+            const double x = __dadd_rn(__dsub_rn((double)o.x, (double)me.x), sx);
+            const double y = __dadd_rn(__dsub_rn((double)o.y, (double)me.y), sy);
+            const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+            const double q = __ddiv_rn(__dadd_rn(__dmul_rn(cs, x), __dmul_rn(sn, y)), dist);
+            const double angle = __ddiv_rn(__dmul_rn(acos(q), 180.0), M_PI);
+            if (angle < (double)a.fov_half && dist < a.r) count++;
+        }
+    }
+    a.out[a.cold1[i].w - a.id_base] = count;
+}
+
+__global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) s += q[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// feed(inds,id,...) for an explicit id list, sequentially (fish_mod.cpp:560-574); API completeness, not hot
+struct FeedArgs {
+    float4* cold0; int4* cold1; const float4* rec; const int* cell; const int* ids; int k;
+    uint8_t* quality; int n, nx, qcols, id_base; int* pos_of_id;
+};
+__global__ void index_by_id_kernel(const int4* cold1, int n, int id_base, int* pos_of_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos_of_id[cold1[i].w - id_base] = i;
+}
+__global__ void feed_list_kernel(const FeedArgs a) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int t = 0; t < a.k; ++t) {
+        const int id = a.ids[t];
+        if (id < 0 || id >= a.n) continue;
+        const int i = a.pos_of_id[id];
+        const float4 r = a.rec[i];
+        const int c = a.cell[i];
+        const int gx = (c % a.nx) * FOOD_PER_CELL + min((int)r.x / FOOD_I, FOOD_PER_CELL - 1);
+        const int gy = (c / a.nx) * FOOD_PER_CELL + min((int)r.y / FOOD_I, FOOD_PER_CELL - 1);
+        const int qi = gy * a.qcols + gx;
+        const int q = a.quality[qi];
+        float4 c0 = a.cold0[i];
+        int4 c1 = a.cold1[i];
+        if (q > 0) { c0.z = 0.5f; a.quality[qi] = (uint8_t)(q - 1); c1.z += 1; c1.y = 30; }
+        else c1.y = 0;
+        a.cold0[i] = c0; a.cold1[i] = c1;
+    }
+}
+
+}  // namespace fishk

@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's operator interface for the per-step agent update
+(fish_mod.cpp:64-82: initialize, move, sample, feed, social, in_zone, get_speed, averageturn, ...), bound to
+libfishabm.so through its C ABI.  Arrays use the reference's `individuals` layout (float64 / int32, id order)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class FishAbmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fishabm error {code}: {msg}")
+        self.code = code
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class School:
+    """One school resident on one GPU.  Method names follow the reference's functions."""
+
+    def __init__(self, n: int = 60, w: int = 2000, h: int = 2000, seed: int = 0, device: int = 0,
+                 rolling: bool = True, speed_norm: float = 0.0, mode: int = _lib.MODE_CELL_FP32):
+        self.L = _lib.load()
+        p = _lib.Params()
+        self.L.fishabm_params_default(C.byref(p))
+        p.n, p.w, p.h, p.seed, p.device, p.rolling, p.speed_norm, p.mode = n, w, h, seed, device, int(rolling), speed_norm, mode
+        self.params = p
+        self.ctx = C.c_void_p()
+        rc = self.L.fishabm_create(C.byref(p), C.byref(self.ctx))
+        if rc != 0:
+            raise FishAbmError(rc, self.L.fishabm_last_error(None).decode())
+        self.n, self.w, self.h = n, w, h
+        self.rows, self.cols = h // 20, w // 20
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.L.fishabm_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise FishAbmError(rc, self.L.fishabm_last_error(self.ctx).decode())
+
+    # ---- state -------------------------------------------------------------------------------------------
+    def set_state(self, coords, dir, speed, speed_factor, lag, sample_rate, food_intake):
+        f = lambda a: np.ascontiguousarray(a, np.float64)
+        i = lambda a: np.ascontiguousarray(a, np.int32)
+        coords, dir, speed, speed_factor = f(coords).reshape(-1, 2), f(dir), f(speed), f(speed_factor)
+        lag, sample_rate, food_intake = i(lag), i(sample_rate), i(food_intake)
+        assert coords.shape[0] == dir.shape[0] == self.n
+        self._ck(self.L.fishabm_set_state(self.ctx, _p(coords), _p(dir), _p(speed), _p(speed_factor), _p(lag),
+                                          _p(sample_rate), _p(food_intake)))
+
+    def get_state(self) -> dict:
+        n = self.n
+        out = dict(coords=np.empty((n, 2)), dir=np.empty(n), speed=np.empty(n), speed_factor=np.empty(n),
+                   lag=np.empty(n, np.int32), sample_rate=np.empty(n, np.int32), food_intake=np.empty(n, np.int32))
+        self._ck(self.L.fishabm_get_state(self.ctx, *(_p(out[k]) for k in
+                                                      ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake"))))
+        return out
+
+    def initialize(self, speed: float = 5.0):
+        """initialize(fish, num, 2, speed, struc), fish_mod.cpp:116,183-206"""
+        self._ck(self.L.fishabm_initialize(self.ctx, float(speed)))
+
+    # ---- food grid -----------------------------------------------------------------------------------------
+    def set_quality(self, q):
+        q = np.ascontiguousarray(q, np.int32)
+        self._ck(self.L.fishabm_set_quality(self.ctx, _p(q), q.shape[0], q.shape[1], q.shape[1]))
+
+    def get_quality(self) -> np.ndarray:
+        q = np.empty((self.rows, self.cols), np.int32)
+        self._ck(self.L.fishabm_get_quality(self.ctx, 0, _p(q), self.rows, self.cols, self.cols))
+        return q
+
+    def sum_array(self) -> int:
+        """sum_array(quality, struc), fish_mod.cpp:593-601"""
+        s = np.zeros(1, np.int64)
+        self._ck(self.L.fishabm_sum_quality(self.ctx, _p(s)))
+        return int(s[0])
+
+    def get_environment(self, path: str):
+        """get_environment(environment, quality, struc), fish_mod.cpp:603-629 (the CSV parse; painting is viewer-only)"""
+        q = np.zeros((self.rows, self.cols), np.int32)
+        r, c = C.c_int32(0), C.c_int32(0)
+        rc = self.L.fishabm_load_quality_csv(path.encode(), _p(q), self.rows, self.cols, self.cols, C.byref(r), C.byref(c))
+        if rc != 0:
+            raise FishAbmError(rc, f"cannot read {path} as a {self.rows}x{self.cols} grid")
+        self.set_quality(q)
+        return q
+
+    # ---- frozen-state queries --------------------------------------------------------------------------------
+    def in_zone(self, fov: int, r: float) -> np.ndarray:
+        out = np.empty(self.n, np.int32)
+        self._ck(self.L.fishabm_in_zone(self.ctx, int(fov), float(r), _p(out)))
+        return out
+
+    def zone_counts(self) -> np.ndarray:
+        out = np.empty((self.n, 4), np.int32)
+        self._ck(self.L.fishabm_zone_counts(self.ctx, _p(out)))
+        return out
+
+    def social(self):
+        turn = np.empty(self.n)
+        na, nl, nt = (np.empty(self.n, np.int32) for _ in range(3))
+        self._ck(self.L.fishabm_social(self.ctx, _p(turn), _p(na), _p(nl), _p(nt)))
+        return turn, na, nl, nt
+
+    def get_speed(self) -> np.ndarray:
+        out = np.empty(self.n)
+        self._ck(self.L.fishabm_get_speed(self.ctx, _p(out)))
+        return out
+
+    # ---- stepping ------------------------------------------------------------------------------------------------
+    def move(self):
+        self._ck(self.L.fishabm_move(self.ctx))
+
+    def sample(self):
+        self._ck(self.L.fishabm_sample(self.ctx))
+
+    def step(self, nsteps: int = 1):
+        self._ck(self.L.fishabm_step(self.ctx, int(nsteps)))
+
+    def feed(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        self._ck(self.L.fishabm_feed(self.ctx, _p(ids), len(ids)))
+
+    def run_logged(self, nsteps: int, log_sumq: bool = True, intake_every: int = 0):
+        sumq = np.zeros(nsteps, np.int64) if log_sumq else None
+        rows = (nsteps + intake_every - 1) // intake_every if intake_every > 0 else 0
+        intake = np.zeros((rows, self.n), np.int32) if rows else None
+        self._ck(self.L.fishabm_run_logged(self.ctx, nsteps, _p(sumq), _p(intake), intake_every))
+        return sumq, intake
+
+    @property
+    def step_index(self) -> int:
+        s = C.c_uint32(0)
+        self.L.fishabm_get_step(self.ctx, C.byref(s))
+        return int(s.value)
+
+    @step_index.setter
+    def step_index(self, v: int):
+        self.L.fishabm_set_step(self.ctx, int(v))
+
+    # ---- introspection ---------------------------------------------------------------------------------------------
+    def draw(self, stream: int, step: int, fish_id: int, a: int, b: int, k: int = 0, replicate: int = 0) -> int:
+        out = C.c_int32(0)
+        self._ck(self.L.fishabm_draw(self.ctx, stream, replicate, step, fish_id, k, a, b, C.byref(out)))
+        return int(out.value)
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float(0)
+        self.L.fishabm_last_step_ms(self.ctx, C.byref(ms))
+        return float(ms.value)
+
+    def last_neighbour_ms(self):
+        ms, k = C.c_float(0), C.c_int32(0)
+        self.L.fishabm_last_neighbour_ms(self.ctx, C.byref(ms), C.byref(k))
+        return float(ms.value), int(k.value)
+
+    def enable_stats(self, on: bool = True):
+        self.L.fishabm_enable_stats(self.ctx, int(on))
+
+    def last_pass_stats(self) -> dict:
+        s = _lib.PassStats()
+        self._ck(self.L.fishabm_last_pass_stats(self.ctx, C.byref(s)))
+        return dict(focal=s.focal, candidates=s.candidates, interacting=s.interacting, rechecked=s.rechecked)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64(0)
+        self.L.fishabm_launch_count(self.ctx, C.byref(v))
+        return int(v.value)
+
+
+def averageturn(v, comb_weight: bool = False) -> float:
+    """averageturn(vec, comb_weight), fish_mod.cpp:379-408"""
+    v = np.ascontiguousarray(v, np.float64)
+    return float(_lib.load().fishabm_averageturn(_p(v), len(v), int(comb_weight)))
+
+
+def correctangle(d: float) -> float:
+    return float(_lib.load().fishabm_correctangle(float(d)))
+
+
+def correct_coords(xy, w: int = 2000, h: int = 2000):
+    a = np.array(xy, np.float64)
+    _lib.load().fishabm_correct_coords(_p(a), w, h)
+    return a

@@ -1,0 +1,165 @@
+/* include/fishabm.h -- C ABI of libfishabm.so, the B200 (sm_100a) implementation of the per-step agent
+ * update of fritzfrancisco/fish_abm.
+ *
+ * The reference has no FFI layer: its operator API is the set of free-function prototypes at
+ * fish_mod.cpp:64-82 over `individuals&`, `Structure` and `int quality[][n_cols]`.  Every entry point
+ * below names the reference function it replaces.  Conventions:
+ *   - extern "C", opaque context, plain pointers and sizes, no C++/torch types;
+ *   - every call returns 0 on success or a negative FISHABM_E_* code and never throws;
+ *     fishabm_last_error() gives the message;
+ *   - the library owns all device memory; host buffers are borrowed for the duration of the call and use
+ *     the reference's own layout (class individuals, fish_mod.cpp:35-49): double coords[n][2], double dir[n]
+ *     (degrees, unwrapped), double speed[n], double speed_factor[n], int lag[n], int sample_rate[n],
+ *     int food_intake[n];
+ *   - one context = one school (or one ensemble of independent replicate schools, or one slab of a
+ *     multi-GPU school).  A context is not thread-safe; distinct contexts are independent;
+ *   - calls are synchronous with respect to the host;
+ *   - there is no CPU fallback: without a CUDA device fishabm_create fails with FISHABM_E_CUDA.
+ *
+ * Fixed model constants (literals in the reference): zone radii 15/100/200 (fish_mod.cpp:273-275,543-545),
+ * social field of view 330 deg and front cone 180 deg (:167,589), lag 10 (:548), sample_rate 30/0
+ * (:570,573), distributions choice(0,1) error(-10,10) randomwalk(-45,45) sample(0,35) (:28-33),
+ * food cell 20 units (:56), fed speed_factor 0.5 (:566), combination weights 1.7/0.7 (:385-386).
+ */
+#ifndef FISHABM_H
+#define FISHABM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FISHABM_VERSION 1
+
+enum {
+    FISHABM_OK = 0,
+    FISHABM_E_ARG = -1,     /* bad argument / unsupported geometry */
+    FISHABM_E_CUDA = -2,    /* CUDA runtime error (message has the detail) */
+    FISHABM_E_STATE = -3,   /* call not valid in the current state (e.g. no state uploaded) */
+    FISHABM_E_NOMEM = -4,
+    FISHABM_E_COMM = -5     /* slab exchange error */
+};
+
+enum {
+    FISHABM_MODE_CELL_FP32 = 0,  /* product path: cell list + fused fp32 neighbour kernel with fp64 re-check
+                                    of borderline predicates */
+    FISHABM_MODE_BRUTE_FP64 = 1  /* check mode: all-pairs, fp64, candidate order = id order, literal restatement */
+};
+
+/* random streams = the reference's distributions (fish_mod.cpp:28-33) */
+enum {
+    FISHABM_STREAM_CHOICE = 0, FISHABM_STREAM_ERROR = 1, FISHABM_STREAM_RANDOMWALK = 2,
+    FISHABM_STREAM_QUALITY = 3, FISHABM_STREAM_SEED = 4, FISHABM_STREAM_SAMPLE = 5, FISHABM_STREAM_INIT = 6
+};
+
+typedef struct fishabm_ctx fishabm_ctx;
+
+typedef struct fishabm_params {
+    int32_t struct_size;   /* sizeof(fishabm_params), set by fishabm_params_default */
+    int32_t n;             /* fish per school            (#define num / inds.n, fish_mod.cpp:23,37) */
+    int32_t w, h;          /* world size                 (Structure.w/.h, fish_mod.cpp:58-59); multiples of 200,
+                              at least 600 in cell-list mode */
+    int32_t mode;          /* FISHABM_MODE_* */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t replicates;    /* 1 = one school; >1 = ensemble of independent schools of n fish (w,h = 2000 window each) */
+    int32_t rolling;       /* 1 = get_speed active (the committed reference, fish_mod.cpp:173); 0 = speed_factor only
+                              changes through feed() (the "non-rolling" variant of data/norolling_*) */
+    uint64_t seed;         /* Philox key; draws are addressed by (seed, replicate, step, fish id, stream, k) */
+    double speed_norm;     /* the macro `num` in get_speed (fish_mod.cpp:590); 0 = use n */
+    /* slab decomposition of one school across GPUs (one context per rank); 1 rank = whole world */
+    int32_t rank, nranks;
+    int32_t n_global;      /* fish in the whole school when nranks > 1 (0 = n) */
+    int32_t capacity;      /* per-rank fish capacity when nranks > 1 (0 = automatic) */
+} fishabm_params;
+
+/* pair counters of the most recent neighbour pass (for the roofline accounting) */
+typedef struct fishabm_pass_stats {
+    uint64_t focal;        /* focal fish evaluated */
+    uint64_t candidates;   /* candidate pairs examined (3x3 stencil, j != i) */
+    uint64_t interacting;  /* pairs inside the 330 deg cone and r < 200 that produced a turn */
+    uint64_t rechecked;    /* pairs whose predicates were re-evaluated in fp64 */
+} fishabm_pass_stats;
+
+int fishabm_params_default(fishabm_params* p);
+int fishabm_create(const fishabm_params* p, fishabm_ctx** out);
+void fishabm_destroy(fishabm_ctx* ctx);
+/* message of the last failing call on ctx (ctx == NULL: last fishabm_create failure on this thread) */
+const char* fishabm_last_error(const fishabm_ctx* ctx);
+
+/* ---- state (replaces direct member access on `individuals`, fish_mod.cpp:35-49) --------------------
+ * Arrays hold replicates*n entries, replicate-major.  Any pointer may be NULL in get_state to skip it. */
+int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir, const double* speed,
+                      const double* speed_factor, const int32_t* lag, const int32_t* sample_rate,
+                      const int32_t* food_intake);
+int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* speed, double* speed_factor,
+                      int32_t* lag, int32_t* sample_rate, int32_t* food_intake);
+/* initialize(), fish_mod.cpp:183-206: lag 0, sample_rate 0, speed_factor 1, intake 0, integer heading from
+ * the randomwalk stream, integer-lattice position centre +-100 (from the init stream instead of rand()). */
+int fishabm_initialize(fishabm_ctx* ctx, double speed);
+
+/* ---- food grid (int quality[][n_cols], fish_mod.cpp:119; get_environment :603-629; sum_array :593-601) */
+int fishabm_set_quality(fishabm_ctx* ctx, const int32_t* q, int32_t rows, int32_t cols, int32_t row_stride);
+int fishabm_get_quality(fishabm_ctx* ctx, int32_t replicate, int32_t* q, int32_t rows, int32_t cols, int32_t row_stride);
+int fishabm_sum_quality(fishabm_ctx* ctx, int64_t* sums /* [replicates] */);
+/* parse a quality.csv the way get_environment does (comma separated ints, one row per line) */
+int fishabm_load_quality_csv(const char* path, int32_t* q, int32_t max_rows, int32_t max_cols, int32_t row_stride,
+                             int32_t* rows_out, int32_t* cols_out);
+
+/* ---- frozen-state queries: one result per fish, no mutation ------------------------------------------ */
+/* in_zone(inds,id,fov,r,struc) for every id, fish_mod.cpp:226-260.  r <= 200. */
+int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out);
+/* the four counts of the step: out[id] = { in_zone(330,15), in_zone(330,100), in_zone(330,200), in_zone(180,200) } */
+int fishabm_zone_counts(fishabm_ctx* ctx, int32_t* out4);
+/* social(inds,id,330,struc) for every id, fish_mod.cpp:262-377 (random-walk / tie draws use the current step).
+ * n_* may be NULL. */
+int fishabm_social(fishabm_ctx* ctx, double* turn, int32_t* n_avoid, int32_t* n_align, int32_t* n_attract);
+/* get_speed's value 1 + 2*in_zone(180,200)/num for every id, fish_mod.cpp:588-591, without storing it */
+int fishabm_get_speed(fishabm_ctx* ctx, double* out);
+
+/* ---- stepping ------------------------------------------------------------------------------------------ */
+/* move(inds,struc), fish_mod.cpp:163-181, synchronous form (every fish reads the pre-call state) */
+int fishabm_move(fishabm_ctx* ctx);
+/* sample(inds,quality,env,struc), fish_mod.cpp:540-558 (feeding conflicts resolved lowest id first, as the
+ * reference's id-ordered loop does).  Advances the step counter. */
+int fishabm_sample(fishabm_ctx* ctx);
+/* nsteps x { move; sample } (fish_mod.cpp:126-131) with sample(t) and move(t+1) sharing one neighbour pass;
+ * results are bit-identical to calling fishabm_move / fishabm_sample alternately. */
+int fishabm_step(fishabm_ctx* ctx, int32_t nsteps);
+/* feed(inds,id,...), fish_mod.cpp:560-574, for the listed ids in the given order */
+int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k);
+/* the reference's commented-out loggers (fish_mod.cpp:132-141,149-154) over nsteps steps:
+ * sumq[t] = sum_array after step t ([nsteps][replicates]); intake rows every `intake_every` steps
+ * ([rows][replicates*n]); either may be NULL. */
+int fishabm_run_logged(fishabm_ctx* ctx, int32_t nsteps, int64_t* sumq, int32_t* intake, int32_t intake_every);
+
+int fishabm_get_step(const fishabm_ctx* ctx, uint32_t* step);
+int fishabm_set_step(fishabm_ctx* ctx, uint32_t step);
+
+/* ---- introspection ----------------------------------------------------------------------------------- */
+/* the integer the library draws for (stream, step, fish id, k) mapped to [a,b] like
+ * std::uniform_int_distribution<int>(a,b) on a 32-bit engine (fish_mod.cpp:27-33) */
+int fishabm_draw(const fishabm_ctx* ctx, int32_t stream, uint32_t replicate, uint32_t step, uint32_t id, uint32_t k,
+                 int32_t a, int32_t b, int32_t* out);
+/* device time of the most recent fishabm_move/sample/step call, CUDA events on the library's stream */
+int fishabm_last_step_ms(const fishabm_ctx* ctx, float* ms);
+/* device time of the neighbour kernel alone, summed over the most recent call, and its launch count */
+int fishabm_last_neighbour_ms(const fishabm_ctx* ctx, float* ms, int32_t* launches);
+int fishabm_last_pass_stats(fishabm_ctx* ctx, fishabm_pass_stats* out);
+/* kernels launched by this context since creation (for the benchmark's gpu_launches) */
+int fishabm_launch_count(const fishabm_ctx* ctx, uint64_t* out);
+/* enable pair counters (small cost) */
+int fishabm_enable_stats(fishabm_ctx* ctx, int32_t on);
+
+/* ---- slab exchange hooks (nranks > 1; the caller moves the packed buffers between ranks, e.g. NCCL) --- */
+/* see INTEGRATION.md; declared in fishabm_slab.h */
+
+/* ---- host-side scalar helpers with the reference's semantics (not on the hot path) ---------------------- */
+double fishabm_averageturn(const double* v, int32_t n, int32_t comb_weight); /* fish_mod.cpp:379-408 */
+double fishabm_correctangle(double dir);                                       /* fish_mod.cpp:410-418 */
+void fishabm_correct_coords(double* xy, int32_t w, int32_t h);                 /* fish_mod.cpp:466-480 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FISHABM_H */
