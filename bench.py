@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Benchmark of the per-step agent update (BASELINE.json: agent-steps/s at 1M and 16M fish on 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--fish F]
+
+One "step" = one reference step (move() then sample(), fish_mod.cpp:130-131) of the whole school.
+  N=1  : workload C3 = 1,000,000 fish, W=H=44,800, quality.csv tiled.
+  N>1  : workload C4 = 16,777,216 fish, W=H=183,200, split into N spatial slabs (one rank per GPU).
+Prints ONE JSON line (rank 0).  `value` is device-timed with the state resident in HBM; `e2e` goes through the
+C ABI with host buffers in the reference's layout, host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP32_LANES_PER_SM = 128
+N_C3 = 1_000_000
+N_C4 = 16_777_216
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flops_alg(cand: float, inter: float) -> float:
+    """13 flops per candidate pair + 20 per interacting pair"""
+    return 13.0 * cand + 20.0 * inter
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def reference_arm(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path on this box's host cores: the compiled, unmodified
+    fish_mod.cpp (oracle/_ref) when present, else the C restatement.  Each step = a bounded sample of the
+    workload: the full per-fish work of move()+sample() for `k` focal fish on the full frozen state."""
+    if rank != 0:
+        return
+    from fish_abm_b200 import synth
+    from oracle.pyoracle import Oracle, RefLib, State
+    n = args.fish or N_C3
+    w = synth.world_size_for(n)
+    d = synth.uniform_state(n, w, w, seed=0x5EED)
+    cores = min(os.cpu_count() or 1, 32)
+    kind = "reference" if (n == N_C3 and RefLib.available(N_C3)) else "port"
+    k = 2 * cores
+    ids = np.random.default_rng(1).choice(n, k, replace=False).astype(np.int32)
+    if kind == "reference":
+        R = RefLib(N_C3)
+        R.set_world(w, w)
+        R.set_state(State(**d))
+        run = lambda: R.time_focal(ids, cores)
+    else:
+        O = Oracle(State(**d), w, w, None, seed=1)
+        run = lambda: O.time_focal(ids)[0]
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    secs = [run() for _ in range(args.steps)]
+    tot = float(np.sum(secs))
+    value = k * args.steps / tot
+    cfg = {"workload": f"C3: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C3 else f"N={n}, W=H={w}",
+           "n_fish": n, "world": w, "l2": "n/a (CPU)"}
+    sample = (f"{k} focal fish per step on the full {n}-fish frozen state, each doing the reference's own per-fish work of "
+              f"move()+sample() (8 all-pairs passes if lag==0 else 3); agent-steps/s = focal fish / seconds (extrapolation, "
+              f"the O(N^2) step itself is ~days)")
+    line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(n, w, d, budget_s=12.0):
+    """bounded CPU timing on rank 0 (N=1 only): see reference_arm"""
+    from oracle.pyoracle import Oracle, RefLib, State
+    cores = min(os.cpu_count() or 1, 32)
+    kind = "reference" if (n == N_C3 and RefLib.available(N_C3)) else "port"
+    if kind == "reference":
+        R = RefLib(N_C3); R.set_world(w, w); R.set_state(State(**d))
+        run = lambda ids: R.time_focal(ids, cores)
+    else:
+        O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, None, seed=1)
+        run = lambda ids: O.time_focal(ids)[0]
+    rng = np.random.default_rng(2)
+    t1 = run(rng.choice(n, cores, replace=False).astype(np.int32))
+    k = int(max(cores, min(64 * cores, cores * budget_s / max(t1, 1e-3))))
+    secs = run(rng.choice(n, k, replace=False).astype(np.int32))
+    return {"value": k / secs, "unit": "agent-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{k} focal fish of the {n}-fish state in {secs:.1f} s on {cores} host threads (per-fish work of move()+sample(): "
+                      f"8 all-pairs passes if lag==0 else 3), extrapolated to agent-steps/s = focal fish / seconds"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from fish_abm_b200 import School, synth
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        from fish_abm_b200.slab import run_slab_bench
+        return run_slab_bench(args, rank, world, local_rank)
+
+    n = args.fish or N_C3
+    w = synth.world_size_for(n)
+    q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+    d = synth.uniform_state(n, w, w, seed=0x5EED)
+    q = synth.tile_quality(q100, w, w)
+    S = School(n=n, w=w, h=w, seed=0x5EED, device=local_rank)
+    S.set_state(**d)
+    S.set_quality(q)
+
+    state_bytes = n * (48 + 4 + 24)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if state_bytes < (200 << 20) else None
+
+    def l2_flush():
+        if flush is not None:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K steps, each timed on the library's stream with CUDA events
+    for _ in range(args.warmup):
+        S.step(1)
+    S.flush()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = S.launch_count()
+    torch.cuda.synchronize()
+    step_ms, nb_ms, nb_launches = [], 0.0, 0
+    for _ in range(args.steps):
+        l2_flush()
+        S.step(1)
+        step_ms.append(S.last_step_ms())
+        a, b = S.last_neighbour_ms(); nb_ms += a; nb_launches += b
+    S.flush()  # the trailing sample() of the last step belongs to the K steps
+    step_ms.append(S.last_step_ms())
+    a, b = S.last_neighbour_ms(); nb_ms += a; nb_launches += b
+    torch.cuda.synchronize()
+    launches = S.launch_count() - launches0
+    clk = clocks.stop()
+    total_ms = float(np.sum(step_ms))
+    value = n * args.steps / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (neighbour_kernel, FP32 pipe): algorithmic flops from exact pair counters
+    S.enable_stats(True)
+    cand = inter = focal = 0.0
+    reps = 4
+    for _ in range(reps):
+        S.step(1)
+        st = S.last_pass_stats()
+        cand += st["candidates"]; inter += st["interacting"]; focal += st["focal"]
+    S.flush()
+    S.enable_stats(False)
+    cand /= reps; inter /= reps; focal /= reps
+    peaks, how = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    per_launch_ms = nb_ms / max(nb_launches, 1)
+    achieved = flops_alg(cand, inter) / (per_launch_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "kernel": "neighbour_kernel", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak, "traffic": None,
+                "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock); FP32 is not in MEASURED_PEAKS.json",
+                "flops_per_launch": flops_alg(cand, inter), "candidates_per_launch": cand, "interacting_per_launch": inter,
+                "focal_per_launch": focal, "launch_ms": per_launch_ms, "share_of_step": nb_ms / total_ms}
+    # the HBM-bound rest of the step (update + counting sort): algorithmic bytes per fish-step, SURVEY 8(d)
+    rest_ms = (total_ms - nb_ms) / args.steps
+    rest_bytes = n * (48 + 28 + 48 + 8 + 8 + 48 + 48 + 4)  # update r/w, pass outputs, rank/cell, scatter r/w
+    roofline_hbm = {"bound": "hbm", "kernels": "update+scan+scatter", "achieved": rest_bytes / (rest_ms * 1e-3) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": rest_bytes / (rest_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms_per_step": rest_ms}
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D of the state and D2H of the result every step
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in S.get_state().items()}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    h2d = sum(v.nbytes for v in host.values())
+    e2e_steps = max(3, min(args.steps, 10))
+    out = {k: torch.empty_like(v).pin_memory().numpy() for k, v in pinned.items()}
+    from fish_abm_b200.school import _p
+    import ctypes as C
+    order = ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake")
+    sumq = np.zeros(1, np.int64)
+
+    def e2e_step():
+        S._ck(S.L.fishabm_set_state(S.ctx, *(_p(host[k]) for k in order)))
+        S._ck(S.L.fishabm_step(S.ctx, 1))
+        S._ck(S.L.fishabm_get_state(S.ctx, *(_p(out[k]) for k in order)))
+        S._ck(S.L.fishabm_sum_quality(S.ctx, _p(sumq)))
+        for k in order:
+            host[k][...] = out[k]
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": n * e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h2d + 8),
+           "steps": e2e_steps, "api": "fishabm_set_state + fishabm_step(1) + fishabm_get_state + fishabm_sum_quality, pinned host buffers"}
+
+    cpu = cpu_baseline_leg(n, w, d) if not args.no_cpu_baseline else None
+    S.close()
+    line = {"metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3: N={n} school, W=H={w} periodic, cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0"
+                       if n == N_C3 else f"N={n} school, W=H={w}", "n_fish": n, "world": w,
+                       "l2": "flushed between steps (256 MiB write)" if flush is not None else "state larger than L2",
+                       "timing": "CUDA events on the library's stream around each fishabm_step(1); K steps + the trailing sample pass"},
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fish", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20
+        return reference_arm(args, rank, world)
+    return ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,7 @@ SYMBOLS = [
     "fishabm_params_default", "fishabm_create", "fishabm_destroy", "fishabm_last_error", "fishabm_set_state",
     "fishabm_get_state", "fishabm_initialize", "fishabm_set_quality", "fishabm_get_quality", "fishabm_sum_quality",
     "fishabm_load_quality_csv", "fishabm_in_zone", "fishabm_zone_counts", "fishabm_social", "fishabm_get_speed",
-    "fishabm_move", "fishabm_sample", "fishabm_step", "fishabm_feed", "fishabm_run_logged", "fishabm_get_step",
+    "fishabm_move", "fishabm_sample", "fishabm_step", "fishabm_flush", "fishabm_feed", "fishabm_run_logged", "fishabm_get_step",
     "fishabm_set_step", "fishabm_draw", "fishabm_last_step_ms", "fishabm_last_neighbour_ms",
     "fishabm_last_pass_stats", "fishabm_launch_count", "fishabm_enable_stats", "fishabm_averageturn",
     "fishabm_correctangle", "fishabm_correct_coords",
@@ -68,6 +68,7 @@ def load():
     L.fishabm_move.argtypes = [vp]
     L.fishabm_sample.argtypes = [vp]
     L.fishabm_step.argtypes = [vp, i32]
+    L.fishabm_flush.argtypes = [vp]
     L.fishabm_feed.argtypes = [vp, vp, i32]
     L.fishabm_run_logged.argtypes = [vp, i32, vp, vp, i32]
     L.fishabm_get_step.argtypes = [vp, C.POINTER(u32)]

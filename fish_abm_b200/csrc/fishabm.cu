@@ -40,6 +40,7 @@ struct fishabm_ctx {
     double speed_norm = 1.0;
     uint32_t step = 0;
     bool have_state = false;
+    bool pending_sample = false;  // sample() of step `step-1` not yet applied (it shares the next move's neighbour pass)
     bool stats_on = false;
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -173,6 +174,17 @@ int need_state(fishabm_ctx* ctx) {
     return 0;
 }
 
+// fishabm_step leaves the last step's sample() pending so that it can share the next move's neighbour pass;
+// anything that observes or replaces state completes it first.
+int flush_pending(fishabm_ctx* ctx, bool timed = false) {
+    if (!ctx->pending_sample) return 0;
+    int rc;
+    if ((rc = neighbour_pass(ctx, 0, true, ctx->step - 1, ctx->step - 1, timed))) return rc;
+    if ((rc = update_pass(ctx, true, false, ctx->step - 1))) return rc;
+    ctx->pending_sample = false;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -278,6 +290,8 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     if (!ctx || !coords || !dir || !speed || !speed_factor || !lag || !sample_rate || !food_intake)
         return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: null argument");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    ctx->pending_sample = false;
     const size_t n = (size_t)ctx->n;
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->st_coords, coords, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -310,6 +324,7 @@ int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* spe
     int rc = need_state(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     const size_t n = (size_t)ctx->n;
     cudaStream_t s = ctx->stream;
     const Buffers& b = ctx->buf[ctx->cur];
@@ -357,6 +372,7 @@ int fishabm_set_quality(fishabm_ctx* ctx, const int32_t* q, int32_t rows, int32_
             ctx->h_q8[(size_t)r * cols + c] = (uint8_t)v;
         }
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(ctx->quality, ctx->h_q8, (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -367,6 +383,7 @@ int fishabm_get_quality(fishabm_ctx* ctx, int32_t replicate, int32_t* q, int32_t
     if (replicate != 0 || rows != ctx->qrows || cols != ctx->qcols || row_stride < cols)
         return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: grid is %d x %d, replicate 0", ctx->qrows, ctx->qcols);
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(ctx->h_q8, ctx->quality, (size_t)rows * cols, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < rows; ++r)
@@ -377,6 +394,7 @@ int fishabm_get_quality(fishabm_ctx* ctx, int32_t replicate, int32_t* q, int32_t
 int fishabm_sum_quality(fishabm_ctx* ctx, int64_t* sums) {
     if (!ctx || !sums) return fail(ctx, FISHABM_E_ARG, "fishabm_sum_quality: null argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     CK(cudaMemsetAsync(ctx->stats + 4, 0, sizeof(unsigned long long), ctx->stream));
     sum_quality_kernel<<<296, 256, 0, ctx->stream>>>(ctx->quality, (size_t)ctx->qrows * ctx->qcols, ctx->stats + 4);
     ctx->launches += 1;
@@ -451,6 +469,7 @@ int fishabm_zone_counts(fishabm_ctx* ctx, int32_t* out4) {
     if (rc) return rc;
     if (!out4) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, out4, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
@@ -460,6 +479,7 @@ int fishabm_social(fishabm_ctx* ctx, double* turn, int32_t* n_avoid, int32_t* n_
     if (rc) return rc;
     if (!turn) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, nullptr, turn, n_avoid, n_align, n_attract, nullptr);
 }
@@ -469,6 +489,7 @@ int fishabm_get_speed(fishabm_ctx* ctx, double* out) {
     if (rc) return rc;
     if (!out) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, out);
 }
@@ -479,6 +500,7 @@ int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out) {
     if (!out) return fail(ctx, FISHABM_E_ARG, "null argument");
     if (!(r <= 200.0) || fov_deg < 0 || fov_deg > 360) return fail(ctx, FISHABM_E_ARG, "fishabm_in_zone: needs r <= 200 and 0 <= fov <= 360");
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     const Buffers& b = ctx->buf[ctx->cur];
     ZoneArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start, ctx->st_lag, ctx->n, ctx->nx, ctx->ny, 0, fov_deg / 2, r};
     in_zone_generic_kernel<<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(a);
@@ -495,6 +517,7 @@ int fishabm_move(fishabm_ctx* ctx) {
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
     if ((rc = begin_timed(ctx))) return rc;
+    if ((rc = flush_pending(ctx, true))) return rc;
     if ((rc = neighbour_pass(ctx, 0, false, ctx->step, ctx->step, true))) return rc;
     if ((rc = update_pass(ctx, false, true, ctx->step))) return rc;
     return end_timed(ctx);
@@ -505,25 +528,31 @@ int fishabm_sample(fishabm_ctx* ctx) {
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
     if ((rc = begin_timed(ctx))) return rc;
-    if ((rc = neighbour_pass(ctx, 0, true, ctx->step, ctx->step, true))) return rc;
-    if ((rc = update_pass(ctx, true, false, ctx->step))) return rc;
-    ctx->step += 1;
+    if (ctx->pending_sample) {  // the step's sample() is the pending one
+        if ((rc = flush_pending(ctx, true))) return rc;
+    } else {
+        if ((rc = neighbour_pass(ctx, 0, true, ctx->step, ctx->step, true))) return rc;
+        if ((rc = update_pass(ctx, true, false, ctx->step))) return rc;
+        ctx->step += 1;
+    }
     return end_timed(ctx);
 }
 
 static int step_untimed(fishabm_ctx* ctx, int nsteps) {
-    // move(s); { sample(s+t-1) + move(s+t) }, t = 1..nsteps-1; sample(s+nsteps-1)
+    // move(s); { sample(s+t-1) + move(s+t) } ...; the trailing sample stays pending (flush_pending)
     int rc;
-    const uint32_t s = ctx->step;
-    if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
-    if ((rc = update_pass(ctx, false, true, s))) return rc;
-    for (int t = 1; t < nsteps; ++t) {
-        if ((rc = neighbour_pass(ctx, 1, true, s + t - 1, s + t, true))) return rc;
-        if ((rc = update_pass(ctx, true, true, s + t))) return rc;
+    for (int t = 0; t < nsteps; ++t) {
+        const uint32_t s = ctx->step;
+        if (ctx->pending_sample) {
+            if ((rc = neighbour_pass(ctx, 1, true, s - 1, s, true))) return rc;
+            if ((rc = update_pass(ctx, true, true, s))) return rc;
+        } else {
+            if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
+            if ((rc = update_pass(ctx, false, true, s))) return rc;
+        }
+        ctx->pending_sample = true;
+        ctx->step = s + 1;
     }
-    if ((rc = neighbour_pass(ctx, 0, true, s + nsteps - 1, s + nsteps - 1, true))) return rc;
-    if ((rc = update_pass(ctx, true, false, s + nsteps - 1))) return rc;
-    ctx->step = s + (uint32_t)nsteps;
     return 0;
 }
 
@@ -534,6 +563,15 @@ int fishabm_step(fishabm_ctx* ctx, int32_t nsteps) {
     CK(cudaSetDevice(ctx->p.device));
     if ((rc = begin_timed(ctx))) return rc;
     if ((rc = step_untimed(ctx, nsteps))) return rc;
+    return end_timed(ctx);
+}
+
+int fishabm_flush(fishabm_ctx* ctx) {
+    int rc = need_state(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->p.device));
+    if ((rc = begin_timed(ctx))) return rc;
+    if ((rc = flush_pending(ctx, true))) return rc;
     return end_timed(ctx);
 }
 
@@ -563,6 +601,7 @@ int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k) {
     if (k > ctx->n) return fail(ctx, FISHABM_E_ARG, "fishabm_feed: at most n ids per call");
     if (k == 0) return 0;
     CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     const Buffers& b = ctx->buf[ctx->cur];
     CK(cudaMemcpyAsync(ctx->st_lag, ids, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     index_by_id_kernel<<<cdiv(ctx->n, 256), 256, 0, ctx->stream>>>(b.cold1, ctx->n, 0, ctx->pos_of_id);

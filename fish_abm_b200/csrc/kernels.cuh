@@ -168,7 +168,7 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
         const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
         bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
-        unc = unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb || fabsf(ca) > 1.f - 1.0e-6f;
+        unc = unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb;
         bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
         if (unc) {
             const uint32_t code = tj[k];

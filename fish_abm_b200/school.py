@@ -138,6 +138,10 @@ class School:
     def step(self, nsteps: int = 1):
         self._ck(self.L.fishabm_step(self.ctx, int(nsteps)))
 
+    def flush(self):
+        """complete the pending sample() of the last step (see include/fishabm.h)"""
+        self._ck(self.L.fishabm_flush(self.ctx))
+
     def feed(self, ids):
         ids = np.ascontiguousarray(ids, np.int32)
         self._ck(self.L.fishabm_feed(self.ctx, _p(ids), len(ids)))

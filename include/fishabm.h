@@ -124,8 +124,11 @@ int fishabm_move(fishabm_ctx* ctx);
  * reference's id-ordered loop does).  Advances the step counter. */
 int fishabm_sample(fishabm_ctx* ctx);
 /* nsteps x { move; sample } (fish_mod.cpp:126-131) with sample(t) and move(t+1) sharing one neighbour pass;
- * results are bit-identical to calling fishabm_move / fishabm_sample alternately. */
+ * results are bit-identical to calling fishabm_move / fishabm_sample alternately (see fishabm_flush). */
 int fishabm_step(fishabm_ctx* ctx, int32_t nsteps);
+/* fishabm_step leaves the sample() of its last step pending so that it can share the neighbour pass of the next
+ * move(); every call that observes or replaces state completes it implicitly, fishabm_flush does so explicitly. */
+int fishabm_flush(fishabm_ctx* ctx);
 /* feed(inds,id,...), fish_mod.cpp:560-574, for the listed ids in the given order */
 int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k);
 /* the reference's commented-out loggers (fish_mod.cpp:132-141,149-154) over nsteps steps:

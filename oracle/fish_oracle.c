@@ -154,6 +154,9 @@ typedef struct {
     int n_avoid, n_align, n_attract; /* as fish_mod.cpp:273-275 */
     int n_ties;                      /* distrib_choice draws consumed (:328, :461) */
     int randomwalk;                  /* 1 if the turn came from distrib_randomwalk (:373) */
+    int knife;                       /* neighbours whose bearing sits on a discontinuity of the turn rule to within
+                                        1e-4 deg (avoid zone: bearing ~ 0; any zone: |bearing| ~ 180): the reference's own
+                                        answer then hinges on fp64 rounding noise, so parity tests skip such fish */
 } orc_social_out;
 
 /* social, fish_mod.cpp:262-377.  Turns are accumulated as running cos/sin sums in candidate order,
@@ -162,7 +165,7 @@ typedef struct {
 void orc_social(const orc_school* S, int id, int fov, uint32_t step, orc_social_out* out) {
     const double fx = S->coords[2 * id], fy = S->coords[2 * id + 1], fdir = S->dir[id];
     const double dx0 = cos(fdir * M_PI / 180), dy0 = sin(fdir * M_PI / 180);
-    int n_av = 0, n_al = 0, n_at = 0, ties = 0;
+    int n_av = 0, n_al = 0, n_at = 0, ties = 0, knife = 0;
     double av_x = 0, av_y = 0, al_x = 0, al_y = 0, at_x = 0, at_y = 0;
     for (int i = 0; i < S->n; ++i) {
         if (i == id) continue;
@@ -175,6 +178,7 @@ void orc_social(const orc_school* S, int id, int fov, uint32_t step, orc_social_
         if (dist < 15) { /* :316-332 */
             double a = getangle_core(fx, fy, fdir, S->coords[2 * i], S->coords[2 * i + 1], S->w, S->h, &tie);
             if (tie) { a = (orc_draw_from(S->seed, S->replicate, step, id, ORC_STREAM_CHOICE, i, 0, 1) - 0.5) * 360; ties++; }
+            if (fabs(a) < 1e-4 || fabs(fabs(a) - 180) < 1e-4) knife++;
             double t;
             if (a > 0) t = a - 180;
             else if (a < 0) t = a + 180;
@@ -188,12 +192,14 @@ void orc_social(const orc_school* S, int id, int fov, uint32_t step, orc_social_
             p[1] = sin(S->dir[i] * M_PI / 180) + fy;
             double a = getangle_core(fx, fy, fdir, p[0], p[1], S->w, S->h, &tie);
             if (tie) { a = (orc_draw_from(S->seed, S->replicate, step, id, ORC_STREAM_CHOICE, i, 0, 1) - 0.5) * 360; ties++; }
+            if (fabs(fabs(a) - 180) < 1e-4) knife++;
             double t = a * (1 / (0.004 * ((dist - 15) * (dist - 15)) + 2));
             al_x = al_x + cos(t * M_PI / 180); al_y = al_y + sin(t * M_PI / 180);
             n_al++;
         } else { /* :345-351 */
             double a = getangle_core(fx, fy, fdir, S->coords[2 * i], S->coords[2 * i + 1], S->w, S->h, &tie);
             if (tie) { a = (orc_draw_from(S->seed, S->replicate, step, id, ORC_STREAM_CHOICE, i, 0, 1) - 0.5) * 360; ties++; }
+            if (fabs(fabs(a) - 180) < 1e-4) knife++;
             double t = a * (1 / (0.004 * ((dist - 200) * (dist - 200)) + 2));
             at_x = at_x + cos(t * M_PI / 180); at_y = at_y + sin(t * M_PI / 180);
             n_at++;
@@ -209,7 +215,7 @@ void orc_social(const orc_school* S, int id, int fov, uint32_t step, orc_social_
     else if (n_at > 0) turn = averageturn_sums(at_x, at_y, n_at);
     else { turn = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_RANDOMWALK, -45, 45); rw = 1; } /* :372-374 */
     out->turn = turn; out->n_avoid = n_av; out->n_align = n_al; out->n_attract = n_at;
-    out->n_ties = ties; out->randomwalk = rw;
+    out->n_ties = ties; out->randomwalk = rw; out->knife = knife;
 }
 
 /* ---- feed / sample ------------------------------------------------------------------------- */
@@ -377,9 +383,9 @@ void orc_run(orc_school* S, int steps, uint32_t first_step, int sync, long* sumq
 }
 
 /* ---- timing leg for bench.py's cpu_baseline ("port") ---------------------------------------------
- * The reference's per-fish work for k focal ids on the full state: social + get_speed's in_zone +
- * 3 in_zone (move) and 3 in_zone (sample) = 8 all-pairs passes per fish-step
- * (fish_mod.cpp:167,173,273-275,543-545), each literally executed.  Returns seconds. */
+ * The reference's per-fish work of one step for k focal ids on the full state: for a moving fish (lag==0)
+ * social + get_speed's in_zone + 3 in_zone, then sample's 3 in_zone = 8 all-pairs passes; 3 for a lagged fish
+ * (fish_mod.cpp:165-179,543-545), each literally executed.  Returns seconds. */
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -397,11 +403,14 @@ double orc_time_focal(const orc_school* S, const int* ids, int k, int* threads_u
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : sink)
     for (int j = 0; j < k; ++j) {
         int id = ids[j];
-        orc_social_out so;
-        orc_social(S, id, 330, 0, &so); /* the pair loop of social, :293-354 */
-        double acc = so.turn;
-        acc += orc_in_zone(S, id, 330, 15) + orc_in_zone(S, id, 330, 100) + orc_in_zone(S, id, 330, 200); /* social :273-275 */
-        acc += orc_in_zone(S, id, 180, 200);                                                                /* get_speed :589 */
+        double acc = 0;
+        if (S->lag[id] == 0) { /* move(): fish_mod.cpp:165-175 */
+            orc_social_out so;
+            orc_social(S, id, 330, 0, &so); /* the pair loop of social, :293-354 */
+            acc += so.turn;
+            acc += orc_in_zone(S, id, 330, 15) + orc_in_zone(S, id, 330, 100) + orc_in_zone(S, id, 330, 200); /* social :273-275 */
+            acc += orc_in_zone(S, id, 180, 200);                                                                /* get_speed :589 */
+        }
         acc += orc_in_zone(S, id, 330, 15) + orc_in_zone(S, id, 330, 100) + orc_in_zone(S, id, 330, 200); /* sample :543-545 */
         sink += acc;
     }
@@ -417,3 +426,10 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ---- exported views of the inline RNG helpers (for tests) ------------------------------------------ */
+void orc_philox_export(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) { orc_philox4x32_10(ctr4, key2, out4); }
+int orc_draw_export(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t id, uint32_t stream, uint32_t k0, int a, int b) {
+    return orc_draw_from(seed, replicate, step, id, stream, k0, a, b);
+}
+int orc_lemire_accept_export(uint32_t word, int a, int b, int* value) { return orc_lemire_accept(word, a, b, value); }

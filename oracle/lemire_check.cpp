@@ -27,5 +27,25 @@ int main(int argc, char** argv) {
             int v = d(e);
             printf("%d %u %u %d %d %d %u\n", ranges[r][0], e.step, e.id, ranges[r][1], ranges[r][2], v, e.k);
         }
+    // crafted first words around the rejection threshold (2^32 mod range): "99 word 0 a b value words_consumed"
+    struct Crafted {
+        typedef uint32_t result_type;
+        uint32_t first; uint32_t k;
+        static constexpr result_type min() { return 0u; }
+        static constexpr result_type max() { return 0xFFFFFFFFu; }
+        result_type operator()() { return k++ == 0 ? first : 0x9E3779B9u * k; }
+    };
+    for (int r = 0; r < 6; ++r) {
+        const uint32_t range = (uint32_t)(ranges[r][2] - ranges[r][1]) + 1u;
+        for (uint32_t w = 0; w < 400; ++w) {
+            const uint32_t firsts[3] = {w, 0xFFFFFFFFu - w, (uint32_t)(((uint64_t)w << 32) / range) + (w & 1)};
+            for (int f = 0; f < 3; ++f) {
+                Crafted e{firsts[f], 0};
+                std::uniform_int_distribution<int> d(ranges[r][1], ranges[r][2]);
+                int v = d(e);
+                printf("99 %u 0 %d %d %d %u\n", firsts[f], ranges[r][1], ranges[r][2], v, e.k);
+            }
+        }
+    }
     return 0;
 }

@@ -70,11 +70,11 @@ class _OrcSchool(C.Structure):
 
 class _SocialOut(C.Structure):
     _fields_ = [("turn", C.c_double), ("n_avoid", C.c_int), ("n_align", C.c_int), ("n_attract", C.c_int),
-                ("n_ties", C.c_int), ("randomwalk", C.c_int), ("pad_", C.c_int)]
+                ("n_ties", C.c_int), ("randomwalk", C.c_int), ("knife", C.c_int)]
 
 
 SOCIAL_DTYPE = np.dtype([("turn", "f8"), ("n_avoid", "i4"), ("n_align", "i4"), ("n_attract", "i4"),
-                         ("n_ties", "i4"), ("randomwalk", "i4"), ("pad_", "i4")])
+                         ("n_ties", "i4"), ("randomwalk", "i4"), ("knife", "i4")])
 assert SOCIAL_DTYPE.itemsize == C.sizeof(_SocialOut)
 
 

@@ -432,17 +432,20 @@ void ref_move_focal(int id, double* out5) {
 
 // ---- timing legs for bench.py's cpu_baseline / --impl reference ------------------------------
 // (a) whole steps: ref_run above returns seconds.
-// (b) N too large for an O(N^2) step: the reference's own per-fish work for `k` focal ids on the
-//     full state = social + 3 in_zone (move) + get_speed's in_zone + 3 in_zone (sample):
-//     8 all-pairs passes, fish_mod.cpp:167,173,273-275,543-545.  Threads each take a share.
+// (b) N too large for an O(N^2) step: the reference's own per-fish work of one step for `k` focal ids on the
+//     full state: if lag==0, social (3 in_zone + pair loop) + get_speed's in_zone; then sample's 3 in_zone:
+//     8 all-pairs passes for a moving fish, 3 for a lagged one (fish_mod.cpp:165-179,543-545).
 struct FocalTimeArg { const int* ids; volatile double sink; };
 static void body_focal_work(int k, void* p) {
     FocalTimeArg* a = (FocalTimeArg*)p;
     int id = a->ids[k];
     g_ctx.mode = HM_FOCAL; g_ctx.focal = id; g_ctx.choice_k = 0;
-    double acc = social(g_inds, id, 330, g_struc);
-    acc += in_zone(g_inds, id, 180, 200, g_struc);
-    acc += in_zone(g_inds, id, 330, 15, g_struc);
+    double acc = 0;
+    if (g_inds.lag[id] == 0) {                       // move(): fish_mod.cpp:165-175
+        acc += social(g_inds, id, 330, g_struc);     //   social = 3 in_zone + the pair loop
+        acc += in_zone(g_inds, id, 180, 200, g_struc); // get_speed
+    }
+    acc += in_zone(g_inds, id, 330, 15, g_struc);    // sample(): fish_mod.cpp:543-545, every fish
     acc += in_zone(g_inds, id, 330, 100, g_struc);
     acc += in_zone(g_inds, id, 330, 200, g_struc);
     a->sink = a->sink + acc;

@@ -1,0 +1,34 @@
+import numpy as np
+
+from fish_abm_b200 import synth
+
+
+def test_world_sizes_of_the_benchmark_configs():
+    assert synth.world_size_for(1_000_000) == 44_800
+    assert synth.world_size_for(16_777_216) == 183_200
+    assert synth.world_size_for(60) == 600
+
+
+def test_uniform_state_is_fp32_representable_and_in_range():
+    d = synth.uniform_state(5000, 4400, 4400, seed=3)
+    c = d["coords"]
+    assert np.array_equal(c.astype(np.float32).astype(np.float64), c)
+    assert c.min() >= 0 and c[:, 0].max() < 4400 and c[:, 1].max() < 4400
+    off = c - 200 * np.floor(c / 200)
+    assert np.array_equal(off.astype(np.float32).astype(np.float64), off)  # in-cell offsets exact too
+    assert set(np.unique(d["lag"])) <= set(range(11))
+    assert 0.5 < (d["lag"] > 0).mean() < 0.7
+    assert d["sample_rate"].min() >= 0 and d["sample_rate"].max() <= 30
+
+
+def test_tile_quality(q100):
+    q = synth.tile_quality(q100, 4400, 2600)
+    assert q.shape == (130, 220)
+    assert np.array_equal(q[:100, :100], q100)
+    assert np.array_equal(q[100:130, 100:200], q100[:30, :])
+
+
+def test_lattice_state_is_integer():
+    d = synth.lattice_state(200, 2000, 2000)
+    assert np.array_equal(d["coords"], np.round(d["coords"]))
+    assert np.abs(d["coords"] - 1000).max() <= 100
