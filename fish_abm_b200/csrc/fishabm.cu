@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "neighbour_v2.cuh"
 
 using namespace fishk;
 
@@ -42,6 +43,7 @@ struct fishabm_ctx {
     bool have_state = false;
     bool pending_sample = false;  // sample() of step `step-1` not yet applied (it shares the next move's neighbour pass)
     bool stats_on = false;
+    int nb_variant = 2;  // neighbour kernel design: 2 = candidate-parallel (default), 1 = focal-parallel (FISHABM_NEIGHBOUR=v1)
     uint64_t launches = 0;
     float last_ms = 0.f;
 
@@ -124,9 +126,15 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         ctx->nb_events_used++;
         CK(cudaEventRecord(e0, ctx->stream));
     }
-    const int grid = cdiv(ctx->ncell, NB_WARPS);
-    if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
-    else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
+    if (ctx->nb_variant == 1) {
+        const int grid = cdiv(ctx->ncell, NB_WARPS);
+        if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
+        else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
+    } else {
+        const int grid = cdiv(ctx->ncell, V2_WARPS);
+        if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+        else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+    }
     ctx->launches += 1;
     if (timed) CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaGetLastError());
@@ -256,6 +264,12 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(cudaMemset(c->stats, 0, 8 * sizeof(unsigned long long)));
         A(cudaMemset(c->aux, 0, n * sizeof(uint32_t)));
     }
+    if (ok) {
+        A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
+    }
+    const char* variant = getenv("FISHABM_NEIGHBOUR");
+    if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
     c->h_q8 = (uint8_t*)malloc(nq > 0 ? nq : 1);
     if (!ok || !c->h_q8) {
         std::string msg = "device allocation failed: " + g_create_error;

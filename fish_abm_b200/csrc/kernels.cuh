@@ -190,7 +190,8 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         const float crossA = fmaf(fc, q.w, -fs * q.z);
         const float dotA = fmaf(fc, q.z, fs * q.w);
         float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
-        if (exotic) beta = getangle_wrap_exotic(beta, dir_raw);
+        bool tie180 = fabsf(beta) >= PI_F;
+        if (exotic) { beta = getangle_wrap_exotic(beta, dir_raw); tie180 = (beta == PI_F); }
         float t = beta;
         if (in15) {
             t = beta - copysignf(PI_F, beta);
@@ -199,7 +200,7 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
                 t = (fishrng::draw(a.seed, a.replicate, a.step_move, my_id, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
                 A.ties++;
             }
-        } else if (al && fabsf(beta) >= PI_F) {  // exactly opposite heading: +-180 at random (fish_mod.cpp:460-462)
+        } else if (al && tie180) {  // exactly opposite heading: +-180 at random (fish_mod.cpp:460-462)
             const uint32_t nid = (uint32_t)a.cold1[tj[k] & 0x0FFFFFFFu].w;
             t = (fishrng::draw(a.seed, a.replicate, a.step_move, my_id, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
             A.ties++;

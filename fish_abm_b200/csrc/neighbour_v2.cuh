@@ -1,0 +1,292 @@
+// K4, second design: candidate-parallel neighbour kernel.
+//
+// One warp owns one focal cell.  The <= 256 candidates of a window batch (the fish of the 3x3 cell stencil, shifted
+// into the focal cell's frame) sit one per lane in registers (8 chunks of 32).  For each ACTIVE focal fish of the
+// cell (broadcast from shared memory):
+//   filter  - every lane tests its candidates with a cheap, conservative, sqrt-free predicate (inside the r=200
+//             disc and not clearly behind the 330 deg cone); survivors are compacted into a per-focal queue in
+//             shared memory with ballot/popc;
+//   process - the queue is consumed 32 entries at a time, one pair per lane, all lanes working for the SAME focal
+//             fish: exact classification (with the fp64 re-check of borderline pairs), zone counts by ballot, and the
+//             avoidance / alignment / attraction turn of the pair accumulated as fixed-point cos/sin in registers;
+//   reduce  - six warp REDUX adds fold the lanes' partial sums into the focal fish's 64-bit accumulators.
+// Lanes therefore stay full regardless of how many fish of the cell are active, and the expensive per-pair math only
+// runs on (almost only) interacting pairs.  Sums are integers, hence independent of candidate order: results are
+// bit-identical to the first design (neighbour_kernel) and across any re-sorting of the fish.
+#pragma once
+#include "kernels.cuh"
+
+namespace fishk {
+
+constexpr int V2_WARPS = 8;
+constexpr int V2_THREADS = V2_WARPS * 32;
+constexpr int V2_WIN = 256;           // candidates per window batch
+constexpr int V2_CH = V2_WIN / 32;    // register chunks per lane
+constexpr int V2_FMAX = 32;           // focal fish per group
+constexpr float V2_FAR = 1.0e18f;     // padding coordinate: fails the disc test
+
+struct V2WarpSmem {
+    float wx[V2_WIN], wy[V2_WIN], wc[V2_WIN], ws[V2_WIN];  // window candidates in the focal cell's frame
+    uint32_t wcode[V2_WIN];                                // sorted index | stencil code << 28
+    long long acc[V2_FMAX][6];                             // fixed-point cos/sin sums: avoid x,y, align x,y, attract x,y
+    int cnt[V2_FMAX][4];                                   // n15, n100, n200, front
+    float4 frec[V2_FMAX];
+    float fdir[V2_FMAX];
+    int fidx[V2_FMAX];
+    int fties[V2_FMAX];
+    unsigned char queue[V2_WIN];
+};
+
+constexpr size_t V2_SMEM_BYTES = sizeof(V2WarpSmem) * V2_WARPS;
+
+// conservative cone test constant: cos^2(165 deg) + margin (see the band analysis in DESIGN.md)
+constexpr float V2_KCONE = 0.93301270189f + 2.5e-4f;
+constexpr float V2_R2HI = (CELL_F + 2.5e-4f) * (CELL_F + 2.5e-4f);
+
+template <bool STATS>
+__global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const NeighArgs a) {
+    extern __shared__ __align__(16) unsigned char v2_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    V2WarpSmem& S = reinterpret_cast<V2WarpSmem*>(v2_smem_raw)[warp];
+
+    const int c = blockIdx.x * V2_WARPS + warp;
+    if (c >= a.ncell) return;
+    const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
+    if (s0 == e0) return;
+    const int cx = c % a.nx, cy = c / a.nx;
+    int nb_s = 0, nb_e = 0;
+    if (lane < 9) {
+        int xx = cx + (lane % 3) - 1, yy = cy + (lane / 3) - 1;
+        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
+        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
+        const int cc = yy * a.nx + xx;
+        nb_s = a.cell_start[cc];
+        nb_e = a.cell_start[cc + 1];
+    }
+    unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
+
+    for (int g0 = s0; g0 < e0; g0 += V2_FMAX) {
+        // ---- focal group: the active fish among 32 consecutive fish of the cell, compacted
+        const int i = g0 + lane;
+        const bool valid = i < e0;
+        float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
+        int4 c1 = make_int4(0, 0, 0, 0);
+        float dir_raw = 0.f;
+        if (valid) { me = a.rec[i]; c1 = a.cold1[i]; dir_raw = a.cold0[i].x; }
+        const bool active = valid && (a.active_lag_max < 0 || c1.x <= a.active_lag_max);
+        const unsigned amask = __ballot_sync(FULL, active);
+        const int nf = __popc(amask);
+        if (valid && !active) a.aux[i] = 0u;
+        if (nf == 0) continue;
+        __syncwarp();
+        if (active) {
+            const int slot = __popc(amask & lt_mask);
+            S.frec[slot] = me; S.fdir[slot] = dir_raw; S.fidx[slot] = i; S.fties[slot] = 0;
+        }
+        for (int t = lane; t < V2_FMAX * 6; t += 32) (&S.acc[0][0])[t] = 0;
+        for (int t = lane; t < V2_FMAX * 4; t += 32) (&S.cnt[0][0])[t] = 0;
+        __syncwarp();
+        if (STATS) st_focal += (unsigned)nf;
+
+        // ---- window batches: the 9 stencil cells' fish are streamed through a WIN-entry window
+        int fill = 0, k = 0;
+        int ks = __shfl_sync(FULL, nb_s, 0), ke = __shfl_sync(FULL, nb_e, 0);
+        int b = ks;
+        bool more = true;
+        while (more) {
+            while (fill < V2_WIN && k < 9) {
+                if (b >= ke) {
+                    ++k;
+                    if (k < 9) { ks = __shfl_sync(FULL, nb_s, k); ke = __shfl_sync(FULL, nb_e, k); b = ks; }
+                    continue;
+                }
+                const float sx = (float)((k % 3) - 1) * CELL_F, sy = (float)((k / 3) - 1) * CELL_F;
+                const int m = min(ke - b, V2_WIN - fill);
+                for (int t = lane; t < m; t += 32) {
+                    const float4 r = __ldg(&a.rec[b + t]);
+                    S.wx[fill + t] = r.x + sx; S.wy[fill + t] = r.y + sy; S.wc[fill + t] = r.z; S.ws[fill + t] = r.w;
+                    S.wcode[fill + t] = (uint32_t)(b + t) | ((uint32_t)k << 28);
+                }
+                fill += m; b += m;
+            }
+            more = (k < 9);
+            if (fill > 0) {
+                // ======== one window batch of `fill` candidates ========
+                __syncwarp();
+                const int nch = (fill + 31) >> 5;
+                float cxr[V2_CH], cyr[V2_CH];
+#pragma unroll
+                for (int ch = 0; ch < V2_CH; ++ch) {
+                    const int j = ch * 32 + lane;
+                    const bool in = j < fill;
+                    cxr[ch] = in ? S.wx[j] : V2_FAR;
+                    cyr[ch] = in ? S.wy[j] : V2_FAR;
+                }
+                for (int f = 0; f < nf; ++f) {
+                    const float4 F = S.frec[f];  // broadcast
+                    const float fx = F.x, fy = F.y, fc = F.z, fs = F.w;
+                    // ---- filter (all candidates, cheap, conservative)
+                    int qn = 0;
+#pragma unroll
+                    for (int ch = 0; ch < V2_CH; ++ch) {
+                        if (ch < nch) {
+                            const float dx = cxr[ch] - fx, dy = cyr[ch] - fy;
+                            const float d2 = fmaf(dx, dx, dy * dy);
+                            const float dot = fmaf(fc, dx, fs * dy);
+                            const bool p = (d2 < V2_R2HI) && ((dot >= 0.f) || (dot * dot < d2 * V2_KCONE) || (d2 < 1.f));
+                            const unsigned bal = __ballot_sync(FULL, p);
+                            if (p) S.queue[qn + __popc(bal & lt_mask)] = (unsigned char)(ch * 32 + lane);
+                            qn += __popc(bal);
+                        }
+                    }
+                    __syncwarp();
+                    if (STATS) st_cand += (unsigned)fill;
+                    // ---- process (compacted pairs, one per lane, same focal fish in every lane)
+                    const float fdir = S.fdir[f];
+                    const bool exotic = fabsf(fdir) >= 540.f;
+                    int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0, ax2 = 0, ay2 = 0;
+                    int n15 = 0, n100 = 0, n200 = 0, nfr = 0, ties = 0;
+                    for (int q0 = 0; q0 < qn; q0 += 32) {
+                        const int e = q0 + lane;
+                        bool live = e < qn;
+                        const int j = live ? (int)S.queue[e] : 0;
+                        const float qx = S.wx[j], qy = S.wy[j];
+                        const float dx = qx - fx, dy = qy - fy;
+                        const float d2 = fmaf(dx, dx, dy * dy);
+                        // d2 == 0: the fish itself or a coincident fish: acos(0/0) is NaN in the reference, the pair is
+                        // dropped from every count (fish_mod.cpp:252-254)
+                        live = live && (d2 > 0.f);
+                        const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+                        const float d = d2 * rinv;
+                        const float dot = fmaf(fc, dx, fs * dy);
+                        const float ca = dot * rinv;
+                        const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
+                        bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
+                        unc = (unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb) && live;
+                        bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
+                        if (unc) {
+                            const uint32_t code = S.wcode[j];
+                            const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
+                            const unsigned bits = exact_pair_bits(fx, fy, fdir, raw.x, raw.y, (int)(code >> 28));
+                            in15 = bits & 1u; in100 = bits & 2u; in200 = bits & 4u; vis = bits & 8u; front = bits & 16u;
+                        }
+                        if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
+                        const bool inter = live && vis && in200;
+                        nfr += __popc(__ballot_sync(FULL, live && front && in200));
+                        n200 += __popc(__ballot_sync(FULL, inter));
+                        n100 += __popc(__ballot_sync(FULL, inter && in100));
+                        n15 += __popc(__ballot_sync(FULL, inter && in15));
+                        if (inter) {
+                            // ---- turn contribution of this neighbour (fish_mod.cpp:316-351), radians
+                            const bool al = in100 && !in15;
+                            const float qc = S.wc[j], qs = S.ws[j];
+                            const float cross = fmaf(fc, dy, -fs * dx);
+                            const float crossA = fmaf(fc, qs, -fs * qc);
+                            const float dotA = fmaf(fc, qc, fs * qs);
+                            float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
+                            bool tie180 = fabsf(beta) >= PI_F;
+                            if (exotic) { beta = getangle_wrap_exotic(beta, fdir); tie180 = (beta == PI_F); }
+                            float t = beta;
+                            if (in15) {
+                                t = beta - copysignf(PI_F, beta);
+                                if (beta == 0.f) {  // dead ahead: +-180 at random (fish_mod.cpp:327-329), keyed by the neighbour's id
+                                    const uint32_t nid = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
+                                    const uint32_t myid = (uint32_t)a.cold1[S.fidx[f]].w;
+                                    t = (fishrng::draw(a.seed, a.replicate, a.step_move, myid, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
+                                    ties++;
+                                }
+                            } else if (al && tie180) {  // exactly opposite heading (fish_mod.cpp:460-462)
+                                const uint32_t nid = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
+                                const uint32_t myid = (uint32_t)a.cold1[S.fidx[f]].w;
+                                t = (fishrng::draw(a.seed, a.replicate, a.step_move, myid, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
+                                ties++;
+                            }
+                            const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
+                            const float kz = in15 ? 0.1f : 0.004f;
+                            const float wgt = __fdividef(1.f, fmaf(kz * ee, ee, 2.f));
+                            const float th = t * wgt;
+                            float sn, cs;
+                            __sincosf(th, &sn, &cs);
+                            const int vx = __float_as_int(cs + FIX_MAGIC) - FIX_MAGIC_BITS;
+                            const int vy = __float_as_int(sn + FIX_MAGIC) - FIX_MAGIC_BITS;
+                            if (in15) { ax0 += vx; ay0 += vy; }
+                            else if (al) { ax1 += vx; ay1 += vy; }
+                            else { ax2 += vx; ay2 += vy; }
+                        }
+                    }
+                    if (STATS) st_inter += (unsigned)n200;
+                    // ---- reduce the lanes' partial sums into the focal fish's accumulators
+                    const int r0 = __reduce_add_sync(FULL, ax0), r1 = __reduce_add_sync(FULL, ay0);
+                    const int r2 = __reduce_add_sync(FULL, ax1), r3 = __reduce_add_sync(FULL, ay1);
+                    const int r4 = __reduce_add_sync(FULL, ax2), r5 = __reduce_add_sync(FULL, ay2);
+                    const int tsum = __reduce_add_sync(FULL, ties);
+                    if (lane < 6) {
+                        const int v = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : lane == 3 ? r3 : lane == 4 ? r4 : r5;
+                        S.acc[f][lane] += (long long)v;
+                    } else if (lane < 10) {
+                        const int v = lane == 6 ? n15 : lane == 7 ? n100 : lane == 8 ? n200 : nfr;
+                        S.cnt[f][lane - 6] += v;
+                    } else if (lane == 10) {
+                        S.fties[f] += tsum;
+                    }
+                    __syncwarp();
+                }
+            }
+            fill = 0;
+        }
+
+        // ---- epilogue, one focal fish per lane: social()'s selection (fish_mod.cpp:355-376), averageturn (:379-408),
+        //      random walk (:372-374) and sample()'s feeding decision (:543-547)
+        __syncwarp();
+        if (lane < nf) {
+            const int f = lane;
+            const int idx = S.fidx[f];
+            const int4 k1 = a.cold1[idx];
+            const int n15 = S.cnt[f][0], n100 = S.cnt[f][1], n200 = S.cnt[f][2], nfr = S.cnt[f][3];
+            const double sx0 = (double)S.acc[f][0], sy0 = (double)S.acc[f][1], sx1 = (double)S.acc[f][2], sy1 = (double)S.acc[f][3];
+            const double sx2 = (double)S.acc[f][4], sy2 = (double)S.acc[f][5];
+            uint32_t aux = AUX_EVALUATED;
+            const int n_av = n15, n_al = n100 - n15, n_at = n200 - n100;
+            double turn;
+            if (n_av > 0) turn = average_from_sums(sx0, sy0);
+            else if (n_al > 0 && n_at > 0) {
+                const double aa = average_from_sums(sx1, sy1) * (M_PI / 180.0);
+                const double tt = average_from_sums(sx2, sy2) * (M_PI / 180.0);
+                double sa, ca, st, ct;
+                sincos(aa, &sa, &ca);
+                sincos(tt, &st, &ct);
+                turn = average_from_sums(1.7 * ca + 0.7 * ct, 1.7 * sa + 0.7 * st);
+            } else if (n_al > 0) turn = average_from_sums(sx1, sy1);
+            else if (n_at > 0) turn = average_from_sums(sx2, sy2);
+            else {
+                turn = (double)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)k1.w, STREAM_RANDOMWALK, 0, -45, 45);
+                aux |= AUX_RANDOMWALK;
+            }
+            aux |= (uint32_t)min(S.fties[f], 127) << AUX_TIE_SHIFT;
+            if (a.do_sample && k1.x == 0) {
+                const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)k1.w, STREAM_SAMPLE, 0, 0, 35);
+                const bool alone = (n_av == 0 && n_al < 5);
+                if (k1.y > dr && !alone) {
+                    const float4 F = S.frec[f];
+                    const int fxl = min((int)F.x / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)F.y / FOOD_I, FOOD_PER_CELL - 1);
+                    aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
+                }
+            }
+            a.cnt[idx] = make_int4(n15, n100, n200, nfr);
+            a.turn[idx] = (float)turn;
+            a.aux[idx] = aux;
+        }
+        __syncwarp();
+    }
+    if (STATS && a.stats) {
+        // st_* are warp-uniform except st_rechk (uniform too: from ballots)
+        if (lane == 0) {
+            atomicAdd(&a.stats[0], st_focal); atomicAdd(&a.stats[1], st_cand);
+            atomicAdd(&a.stats[2], st_inter); atomicAdd(&a.stats[3], st_rechk);
+        }
+    }
+}
+
+}  // namespace fishk

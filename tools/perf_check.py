@@ -1,0 +1,16 @@
+"""Developer timing (GPU box): neighbour kernel designs at the benchmark state."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from fish_abm_b200 import School, synth
+q100 = np.loadtxt(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+n = int(os.environ.get("N", 1_000_000)); w = synth.world_size_for(n)
+d = synth.uniform_state(n, w, w, seed=0x5EED); q = synth.tile_quality(q100, w, w)
+for variant in os.environ.get("VARIANTS", "v1,v2").split(","):
+    os.environ["FISHABM_NEIGHBOUR"] = variant
+    S = School(n=n, w=w, h=w, seed=1); S.set_state(**d); S.set_quality(q)
+    S.step(5); S.flush()
+    for k in (20, 20):
+        S.step(k); ms = S.last_step_ms(); nb, l = S.last_neighbour_ms()
+        print(f"{variant}: N={n} {k} steps {ms:.3f} ms -> {n*k/ms*1e3:.3e} agent-steps/s; neighbour {nb/l*1e3:.1f} us/launch x{l}; rest {(ms-nb)/k*1e3:.1f} us/step", flush=True)
+    S.enable_stats(True); S.step(1); print("   stats", S.last_pass_stats()); S.close()
