@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,8 @@ struct fishabm_ctx {
     int *upd_count = nullptr, *upd_idx = nullptr;
     uint8_t* upd_val = nullptr;
     unsigned long long* stats = nullptr;  // 4 pass counters + 1 scratch for sums
+    int* work_counter = nullptr;
+    int nb_grid = 0;
     int* bad = nullptr;
     int* pos_of_id = nullptr;
     // host<->device staging in the reference's layout
@@ -114,6 +117,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.ncell = ctx->ncell; a.nx = ctx->nx; a.ny = ctx->ny;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = 0;
+    a.work_counter = ctx->work_counter;
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -131,7 +135,8 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
     } else {
-        const int grid = cdiv(ctx->ncell, V2_WARPS);
+        CK(cudaMemsetAsync(ctx->work_counter, 0, sizeof(int), ctx->stream));
+        const int grid = std::min(ctx->nb_grid, cdiv(ctx->ncell, V2_WARPS));
         if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
         else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
     }
@@ -254,7 +259,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->cnt, n)); A(dalloc(&c->turn, n)); A(dalloc(&c->aux, n));
     A(dalloc(&c->quality, nq));
     A(dalloc(&c->upd_count, 1)); A(dalloc(&c->upd_idx, n)); A(dalloc(&c->upd_val, n));
-    A(dalloc(&c->stats, 8)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
+    A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 1)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n));
     if (ok) {
@@ -267,6 +272,12 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (ok) {
         A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
+    }
+    if (ok) {
+        int per_sm = 0, sms = 0;
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
+        A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+        c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");
     if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
@@ -288,7 +299,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     for (int k = 0; k < 2; ++k) { cudaFree(c->buf[k].rec); cudaFree(c->buf[k].cold0); cudaFree(c->buf[k].cold1); cudaFree(c->buf[k].cell); }
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
-    cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->bad); cudaFree(c->pos_of_id);
+    cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4);
     for (auto& pr : c->nb_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

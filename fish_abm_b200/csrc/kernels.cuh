@@ -60,6 +60,7 @@ struct NeighArgs {
     uint32_t step_sample, step_move;
     uint64_t seed;
     uint32_t replicate;
+    int* work_counter;           // zeroed before each launch of the persistent (v2) kernel
 };
 
 // aux bits
@@ -146,6 +147,49 @@ __device__ __forceinline__ void fold_batch(FocalAcc& A) {
 __device__ __forceinline__ double average_from_sums(double x, double y) {
     if (y == 0.0) return (x >= 0.0) ? 0.0 : 180.0;
     return atan2(y, x) * (180.0 / M_PI);
+}
+
+// fp32 form used by the candidate-parallel kernel: integer sums in, degrees out
+__device__ __forceinline__ float average_from_sums_f(long long x, long long y) {
+    if (y == 0) return (x >= 0) ? 0.f : 180.f;
+    return atan2_fast((float)y, (float)x) * (180.f / PI_F);
+}
+
+// Per-fish end of the neighbour pass, shared by both kernel designs: social()'s selection (fish_mod.cpp:355-376),
+// averageturn (:379-408), the random walk (:372-374) and sample()'s feeding decision (:543-547).
+// s[6] = fixed-point cos/sin sums (avoid x,y; align x,y; attract x,y), exact integers.
+__device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k1, float fx, float fy, int n15, int n100, int n200,
+                                             int nfr, const long long* s, int ties) {
+    uint32_t aux = AUX_EVALUATED;
+    const int n_av = n15, n_al = n100 - n15, n_at = n200 - n100;
+    float turn;  // degrees
+    if (n_av > 0) turn = average_from_sums_f(s[0], s[1]);
+    else if (n_al > 0 && n_at > 0) {
+        const float aa = average_from_sums_f(s[2], s[3]) * (PI_F / 180.f);
+        const float tt = average_from_sums_f(s[4], s[5]) * (PI_F / 180.f);
+        float sa, ca, st, ct;
+        __sincosf(aa, &sa, &ca);
+        __sincosf(tt, &st, &ct);
+        const float xs = fmaf(1.7f, ca, 0.7f * ct), ys = fmaf(1.7f, sa, 0.7f * st);
+        turn = (ys == 0.f) ? (xs >= 0.f ? 0.f : 180.f) : atan2_fast(ys, xs) * (180.f / PI_F);
+    } else if (n_al > 0) turn = average_from_sums_f(s[2], s[3]);
+    else if (n_at > 0) turn = average_from_sums_f(s[4], s[5]);
+    else {
+        turn = (float)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)k1.w, STREAM_RANDOMWALK, 0, -45, 45);
+        aux |= AUX_RANDOMWALK;
+    }
+    aux |= (uint32_t)min(ties, 127) << AUX_TIE_SHIFT;
+    if (a.do_sample && k1.x == 0) {  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
+        const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)k1.w, STREAM_SAMPLE, 0, 0, 35);
+        const bool alone = (n_av == 0 && n_al < 5);
+        if (k1.y > dr && !alone) {
+            const int fxl = min((int)fx / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)fy / FOOD_I, FOOD_PER_CELL - 1);
+            aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
+        }
+    }
+    a.cnt[idx] = make_int4(n15, n100, n200, nfr);
+    a.turn[idx] = turn;
+    a.aux[idx] = aux;
 }
 
 template <bool STATS>
@@ -299,38 +343,8 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
         if (!valid) continue;
         if (!active) { a.aux[i] = 0u; continue; }
 
-        // ---- social()'s selection (fish_mod.cpp:355-376) and averageturn (:379-408)
-        uint32_t aux = AUX_EVALUATED;
-        const int n_av = A.n15, n_al = A.n100 - A.n15, n_at = A.n200 - A.n100;
-        double turn;
-        if (n_av > 0) turn = average_from_sums(A.sx0, A.sy0);
-        else if (n_al > 0 && n_at > 0) {
-            const double aa = average_from_sums(A.sx1, A.sy1) * (M_PI / 180.0);
-            const double tt = average_from_sums(A.sx2, A.sy2) * (M_PI / 180.0);
-            double sa, ca, st, ct;
-            sincos(aa, &sa, &ca);
-            sincos(tt, &st, &ct);
-            turn = average_from_sums(1.7 * ca + 0.7 * ct, 1.7 * sa + 0.7 * st);
-        } else if (n_al > 0) turn = average_from_sums(A.sx1, A.sy1);
-        else if (n_at > 0) turn = average_from_sums(A.sx2, A.sy2);
-        else {
-            turn = (double)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_RANDOMWALK, 0, -45, 45);
-            aux |= AUX_RANDOMWALK;
-        }
-        aux |= (uint32_t)min(A.ties, 127) << AUX_TIE_SHIFT;
-
-        // ---- sample()'s decision (fish_mod.cpp:543-547); the draw is only consumed when lag == 0
-        if (a.do_sample && c1.x == 0) {
-            const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)c1.w, STREAM_SAMPLE, 0, 0, 35);
-            const bool alone = (n_av == 0 && n_al < 5);
-            if (c1.y > dr && !alone) {
-                const int fxl = min((int)me.x / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)me.y / FOOD_I, FOOD_PER_CELL - 1);
-                aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
-            }
-        }
-        a.cnt[i] = make_int4(A.n15, A.n100, A.n200, A.nf);
-        a.turn[i] = (float)turn;
-        a.aux[i] = aux;
+        const long long sums[6] = {(long long)A.sx0, (long long)A.sy0, (long long)A.sx1, (long long)A.sy1, (long long)A.sx2, (long long)A.sy2};
+        finish_focal(a, i, c1, me.x, me.y, A.n15, A.n100, A.n200, A.nf, sums, A.ties);
     }
 }
 

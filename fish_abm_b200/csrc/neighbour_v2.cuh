@@ -51,10 +51,15 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
     const unsigned lt_mask = (1u << lane) - 1u;
     V2WarpSmem& S = reinterpret_cast<V2WarpSmem*>(v2_smem_raw)[warp];
 
-    const int c = blockIdx.x * V2_WARPS + warp;
-    if (c >= a.ncell) return;
+    unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
+    // persistent warps: cells are handed out in order by an atomic counter (work per cell varies with occupancy)
+    while (true) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(a.work_counter, 1);
+    c = __shfl_sync(FULL, c, 0);
+    if (c >= a.ncell) break;
     const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
-    if (s0 == e0) return;
+    if (s0 == e0) continue;
     const int cx = c % a.nx, cy = c / a.nx;
     int nb_s = 0, nb_e = 0;
     if (lane < 9) {
@@ -65,7 +70,6 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
         nb_s = a.cell_start[cc];
         nb_e = a.cell_start[cc + 1];
     }
-    unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
 
     for (int g0 = s0; g0 < e0; g0 += V2_FMAX) {
         // ---- focal group: the active fish among 32 consecutive fish of the cell, compacted
@@ -83,15 +87,14 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
         __syncwarp();
         if (active) {
             const int slot = __popc(amask & lt_mask);
-            S.frec[slot] = me; S.fdir[slot] = dir_raw; S.fidx[slot] = i; S.fties[slot] = 0;
+            S.frec[slot] = me; S.fdir[slot] = dir_raw; S.fidx[slot] = i;
         }
-        for (int t = lane; t < V2_FMAX * 6; t += 32) (&S.acc[0][0])[t] = 0;
-        for (int t = lane; t < V2_FMAX * 4; t += 32) (&S.cnt[0][0])[t] = 0;
         __syncwarp();
         if (STATS) st_focal += (unsigned)nf;
 
         // ---- window batches: the 9 stencil cells' fish are streamed through a WIN-entry window
         int fill = 0, k = 0;
+        bool first_batch = true;
         int ks = __shfl_sync(FULL, nb_s, 0), ke = __shfl_sync(FULL, nb_e, 0);
         int b = ks;
         bool more = true;
@@ -135,7 +138,9 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                             const float dx = cxr[ch] - fx, dy = cyr[ch] - fy;
                             const float d2 = fmaf(dx, dx, dy * dy);
                             const float dot = fmaf(fc, dx, fs * dy);
-                            const bool p = (d2 < V2_R2HI) && ((dot >= 0.f) || (dot * dot < d2 * V2_KCONE) || (d2 < 1.f));
+                            // inside the disc, and not clearly behind the cone: dot > -|cos165| d, written sqrt-free with the
+                            // signed square; the +1 keeps every pair closer than 1 unit (its rounding band is wide)
+                            const bool p = (d2 < V2_R2HI) && (fmaf(V2_KCONE, d2, dot * fabsf(dot)) > -1.0f);
                             const unsigned bal = __ballot_sync(FULL, p);
                             if (p) S.queue[qn + __popc(bal & lt_mask)] = (unsigned char)(ch * 32 + lane);
                             qn += __popc(bal);
@@ -174,10 +179,10 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                         }
                         if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
                         const bool inter = live && vis && in200;
-                        nfr += __popc(__ballot_sync(FULL, live && front && in200));
-                        n200 += __popc(__ballot_sync(FULL, inter));
-                        n100 += __popc(__ballot_sync(FULL, inter && in100));
-                        n15 += __popc(__ballot_sync(FULL, inter && in15));
+                        nfr += (live && front && in200) ? 1 : 0;
+                        n200 += inter ? 1 : 0;
+                        n100 += (inter && in100) ? 1 : 0;
+                        n15 += (inter && in15) ? 1 : 0;
                         if (inter) {
                             // ---- turn contribution of this neighbour (fish_mod.cpp:316-351), radians
                             const bool al = in100 && !in15;
@@ -216,24 +221,31 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                             else { ax2 += vx; ay2 += vy; }
                         }
                     }
-                    if (STATS) st_inter += (unsigned)n200;
-                    // ---- reduce the lanes' partial sums into the focal fish's accumulators
+                    // ---- reduce the lanes' partial sums; lane 0 owns the focal fish's accumulators
                     const int r0 = __reduce_add_sync(FULL, ax0), r1 = __reduce_add_sync(FULL, ay0);
                     const int r2 = __reduce_add_sync(FULL, ax1), r3 = __reduce_add_sync(FULL, ay1);
                     const int r4 = __reduce_add_sync(FULL, ax2), r5 = __reduce_add_sync(FULL, ay2);
+                    const int c15 = __reduce_add_sync(FULL, n15), c100 = __reduce_add_sync(FULL, n100);
+                    const int c200 = __reduce_add_sync(FULL, n200), cfr = __reduce_add_sync(FULL, nfr);
                     const int tsum = __reduce_add_sync(FULL, ties);
-                    if (lane < 6) {
-                        const int v = lane == 0 ? r0 : lane == 1 ? r1 : lane == 2 ? r2 : lane == 3 ? r3 : lane == 4 ? r4 : r5;
-                        S.acc[f][lane] += (long long)v;
-                    } else if (lane < 10) {
-                        const int v = lane == 6 ? n15 : lane == 7 ? n100 : lane == 8 ? n200 : nfr;
-                        S.cnt[f][lane - 6] += v;
-                    } else if (lane == 10) {
-                        S.fties[f] += tsum;
+                    if (STATS) st_inter += (unsigned)c200;
+                    if (lane == 0) {
+                        if (first_batch) {
+                            S.acc[f][0] = r0; S.acc[f][1] = r1; S.acc[f][2] = r2; S.acc[f][3] = r3; S.acc[f][4] = r4; S.acc[f][5] = r5;
+                            *reinterpret_cast<int4*>(&S.cnt[f][0]) = make_int4(c15, c100, c200, cfr);
+                            S.fties[f] = tsum;
+                        } else {
+                            S.acc[f][0] += r0; S.acc[f][1] += r1; S.acc[f][2] += r2; S.acc[f][3] += r3; S.acc[f][4] += r4; S.acc[f][5] += r5;
+                            int4 cc = *reinterpret_cast<int4*>(&S.cnt[f][0]);
+                            cc.x += c15; cc.y += c100; cc.z += c200; cc.w += cfr;
+                            *reinterpret_cast<int4*>(&S.cnt[f][0]) = cc;
+                            S.fties[f] += tsum;
+                        }
                     }
                     __syncwarp();
                 }
             }
+            if (fill > 0) first_batch = false;
             fill = 0;
         }
 
@@ -245,41 +257,12 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
             const int idx = S.fidx[f];
             const int4 k1 = a.cold1[idx];
             const int n15 = S.cnt[f][0], n100 = S.cnt[f][1], n200 = S.cnt[f][2], nfr = S.cnt[f][3];
-            const double sx0 = (double)S.acc[f][0], sy0 = (double)S.acc[f][1], sx1 = (double)S.acc[f][2], sy1 = (double)S.acc[f][3];
-            const double sx2 = (double)S.acc[f][4], sy2 = (double)S.acc[f][5];
-            uint32_t aux = AUX_EVALUATED;
-            const int n_av = n15, n_al = n100 - n15, n_at = n200 - n100;
-            double turn;
-            if (n_av > 0) turn = average_from_sums(sx0, sy0);
-            else if (n_al > 0 && n_at > 0) {
-                const double aa = average_from_sums(sx1, sy1) * (M_PI / 180.0);
-                const double tt = average_from_sums(sx2, sy2) * (M_PI / 180.0);
-                double sa, ca, st, ct;
-                sincos(aa, &sa, &ca);
-                sincos(tt, &st, &ct);
-                turn = average_from_sums(1.7 * ca + 0.7 * ct, 1.7 * sa + 0.7 * st);
-            } else if (n_al > 0) turn = average_from_sums(sx1, sy1);
-            else if (n_at > 0) turn = average_from_sums(sx2, sy2);
-            else {
-                turn = (double)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)k1.w, STREAM_RANDOMWALK, 0, -45, 45);
-                aux |= AUX_RANDOMWALK;
-            }
-            aux |= (uint32_t)min(S.fties[f], 127) << AUX_TIE_SHIFT;
-            if (a.do_sample && k1.x == 0) {
-                const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)k1.w, STREAM_SAMPLE, 0, 0, 35);
-                const bool alone = (n_av == 0 && n_al < 5);
-                if (k1.y > dr && !alone) {
-                    const float4 F = S.frec[f];
-                    const int fxl = min((int)F.x / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)F.y / FOOD_I, FOOD_PER_CELL - 1);
-                    aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
-                }
-            }
-            a.cnt[idx] = make_int4(n15, n100, n200, nfr);
-            a.turn[idx] = (float)turn;
-            a.aux[idx] = aux;
+            const float4 F = S.frec[f];
+            finish_focal(a, idx, k1, F.x, F.y, n15, n100, n200, nfr, &S.acc[f][0], S.fties[f]);
         }
         __syncwarp();
     }
+    }  // persistent loop
     if (STATS && a.stats) {
         // st_* are warp-uniform except st_rechk (uniform too: from ballots)
         if (lane == 0) {
