@@ -17,7 +17,15 @@ class Params(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
                 ("mode", C.c_int32), ("device", C.c_int32), ("replicates", C.c_int32), ("rolling", C.c_int32),
                 ("seed", C.c_uint64), ("speed_norm", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("n_global", C.c_int32), ("capacity", C.c_int32)]
+                ("n_global", C.c_int32), ("capacity", C.c_int32), ("halo_capacity", C.c_int32),
+                ("migrant_capacity", C.c_int32), ("force_slab", C.c_int32)]
+
+
+class SlabInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("col0", C.c_int32), ("col1", C.c_int32), ("owned", C.c_int32), ("held", C.c_int32),
+                ("capacity", C.c_int32), ("halo_capacity", C.c_int32), ("migrant_capacity", C.c_int32),
+                ("message_bytes", C.c_int64)]
 
 
 class PassStats(C.Structure):
@@ -34,7 +42,10 @@ SYMBOLS = [
     "fishabm_set_step", "fishabm_draw", "fishabm_last_step_ms", "fishabm_last_neighbour_ms",
     "fishabm_last_pass_stats", "fishabm_launch_count", "fishabm_enable_stats", "fishabm_averageturn",
     "fishabm_correctangle", "fishabm_correct_coords",
+    "fishabm_slab_get_info", "fishabm_slab_unique_id", "fishabm_slab_connect", "fishabm_slab_begin_step",
+    "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy",
 ]
+UNIQUE_ID_BYTES = 128
 
 _lib = None
 
@@ -85,5 +96,12 @@ def load():
     L.fishabm_correctangle.restype = dbl
     L.fishabm_correct_coords.argtypes = [vp, i32, i32]
     L.fishabm_correct_coords.restype = None
+    L.fishabm_slab_get_info.argtypes = [vp, C.POINTER(SlabInfo)]
+    L.fishabm_slab_unique_id.argtypes = [vp, i32]
+    L.fishabm_slab_connect.argtypes = [vp, vp, i32]
+    L.fishabm_slab_begin_step.argtypes = [vp]
+    L.fishabm_slab_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.fishabm_slab_end_step.argtypes = [vp]
+    L.fishabm_slab_copy.argtypes = [vp, vp, C.c_int64]
     _lib = L
     return L

@@ -3,6 +3,7 @@
 #include "../../include/fishabm.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -33,12 +34,28 @@ struct Buffers {  // one set of cell-sorted arrays
 
 struct fishabm_ctx {
     fishabm_params p;
-    std::string err;
+    std::string err_msg;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> nb_events;  // around each neighbour kernel of the last call
     int nb_events_used = 0;
-    int n = 0, nx = 0, ny = 0, ncell = 0, qrows = 0, qcols = 0;
+    int n = 0;            // fish ids are 0..n-1 (the whole school, also in slab mode)
+    int cap = 0;          // entries the sorted arrays can hold (= n for a whole school)
+    Grid g;               // local grid (kernels.cuh)
+    int ncell = 0, qrows = 0, qcols = 0;   // local cells; food grid held here: qrows x qcols (owned columns)
+    int qcols_g = 0, qcol0 = 0;            // global food columns; first owned food column
+    bool slab = false;    // halo columns + message path
+    int own = 0, col0 = 0, left = 0, right = 0;
+    int cap_m = 0, cap_g = 0;
+    size_t msg_bytes = 0;
+    unsigned char *out_left = nullptr, *out_right = nullptr, *in_left = nullptr, *in_right = nullptr;
+    void* comm = nullptr;  // ncclComm_t once connected
+    bool step_open = false;  // between fishabm_slab_begin_step and fishabm_slab_end_step
+    int* n_unsorted = nullptr;
+    int* err = nullptr;
+    int h_n = 0;
+    std::vector<int> h_ids;
+    std::vector<char> h_tmp;
     double speed_norm = 1.0;
     uint32_t step = 0;
     bool have_state = false;
@@ -64,7 +81,7 @@ struct fishabm_ctx {
     int* pos_of_id = nullptr;
     // host<->device staging in the reference's layout
     double *st_coords = nullptr, *st_dir = nullptr, *st_speed = nullptr, *st_sf = nullptr;
-    int *st_lag = nullptr, *st_rate = nullptr, *st_intake = nullptr, *st_i4 = nullptr;
+    int *st_lag = nullptr, *st_rate = nullptr, *st_intake = nullptr, *st_i4 = nullptr, *st_ids = nullptr;
     uint8_t* h_q8 = nullptr;
 };
 
@@ -76,7 +93,7 @@ int fail(fishabm_ctx* c, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(b, sizeof b, fmt, ap);
     va_end(ap);
-    if (c) c->err = b; else g_create_error = b;
+    if (c) c->err_msg = b; else g_create_error = b;
     return code;
 }
 
@@ -90,6 +107,50 @@ template <class T> cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- NCCL, loaded on demand (only slab contexts that call fishabm_slab_connect need it).  The handful of
+// declarations below restate the public NCCL 2.x C API so that building the library does not need nccl.h.
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+constexpr int NCCL_UINT8 = 1;  // ncclUint8
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.h || !api.why.empty()) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+    if (!api.h) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+    auto sym = [&](const char* n) { void* f = dlsym(api.h, n); if (!f && api.why.empty()) api.why = std::string("libnccl lacks ") + n; return f; };
+    api.GetUniqueId = (int (*)(NcclUniqueId*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    api.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!api.why.empty()) { dlclose(api.h); api.h = nullptr; }
+    return api;
+}
+
+#define NK(call)                                                                                                   \
+    do {                                                                                                           \
+        int r_ = (call);                                                                                           \
+        if (r_ != 0) return fail(ctx, FISHABM_E_COMM, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r_) : "nccl error"); \
+    } while (0)
+
+SlabMsg msg(const fishabm_ctx* c, unsigned char* base) { return SlabMsg{base, c->cap_m, c->cap_g}; }
+
 // ---- the counting sort: counts (already accumulated in cell_count) -> cell_start; scatter cur -> other
 int rebuild(fishabm_ctx* ctx) {
     const int ntiles = cdiv(ctx->ncell, SCAN_TILE);
@@ -98,8 +159,8 @@ int rebuild(fishabm_ctx* ctx) {
     scan_finish_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start);
     const Buffers& in = ctx->buf[ctx->cur];
     const Buffers& out = ctx->buf[ctx->cur ^ 1];
-    ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n};
-    scatter_kernel<<<cdiv(ctx->n, 256), 256, 0, ctx->stream>>>(s);
+    ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted};
+    scatter_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(s);
     ctx->launches += 4;
     ctx->cur ^= 1;
     CK(cudaGetLastError());
@@ -114,7 +175,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     NeighArgs a;
     a.rec = b.rec; a.cold0 = b.cold0; a.cold1 = b.cold1; a.cell_start = ctx->cell_start;
     a.cnt = ctx->cnt; a.turn = ctx->turn; a.aux = ctx->aux; a.stats = ctx->stats_on ? ctx->stats : nullptr;
-    a.ncell = ctx->ncell; a.nx = ctx->nx; a.ny = ctx->ny;
+    a.g = ctx->g;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = 0;
     a.work_counter = ctx->work_counter;
@@ -130,13 +191,14 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         ctx->nb_events_used++;
         CK(cudaEventRecord(e0, ctx->stream));
     }
+    const int own_cells = ctx->g.own_c1 - ctx->g.own_c0;
     if (ctx->nb_variant == 1) {
-        const int grid = cdiv(ctx->ncell, NB_WARPS);
+        const int grid = cdiv(own_cells, NB_WARPS);
         if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
     } else {
         CK(cudaMemsetAsync(ctx->work_counter, 0, sizeof(int), ctx->stream));
-        const int grid = std::min(ctx->nb_grid, cdiv(ctx->ncell, V2_WARPS));
+        const int grid = std::min(ctx->nb_grid, cdiv(own_cells, V2_WARPS));
         if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
         else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
     }
@@ -146,18 +208,25 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     return 0;
 }
 
-// K5 (+ deferred food-grid writes, + re-sort when fish moved)
-int update_pass(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
+// K5 (+ deferred food-grid writes); a move also packs the slab messages
+int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
     const Buffers& b = ctx->buf[ctx->cur];
     UpdateArgs u;
     u.rec = b.rec; u.cold0 = b.cold0; u.cold1 = b.cold1; u.cell = b.cell; u.cell_start = ctx->cell_start;
     u.cnt = ctx->cnt; u.turn = ctx->turn; u.aux = ctx->aux;
     u.next_cell = ctx->next_cell; u.next_rank = ctx->next_rank; u.next_count = ctx->cell_count;
     u.quality = ctx->quality; u.upd_count = ctx->upd_count; u.upd_idx = ctx->upd_idx; u.upd_val = ctx->upd_val;
-    u.n = ctx->n; u.nx = ctx->nx; u.ny = ctx->ny; u.qcols = ctx->qcols;
+    u.err = ctx->err;
+    u.g = ctx->g; u.qcols = ctx->qcols;
     u.do_sample = do_sample; u.do_move = do_move; u.rolling = ctx->p.rolling;
     u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = 0; u.speed_norm = ctx->speed_norm;
-    update_kernel<<<cdiv(ctx->n, 256), 256, 0, ctx->stream>>>(u);
+    u.slab = ctx->slab ? 1 : 0;
+    u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
+    if (ctx->slab && do_move) {
+        CK(cudaMemsetAsync(ctx->out_left, 0, sizeof(SlabHeader), ctx->stream));
+        CK(cudaMemsetAsync(ctx->out_right, 0, sizeof(SlabHeader), ctx->stream));
+    }
+    update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
     if (do_sample) {
         apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count, ctx->upd_idx, ctx->upd_val);
@@ -165,8 +234,44 @@ int update_pass(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_mo
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
-    if (do_move) return rebuild(ctx);
     return 0;
+}
+
+// after a move: (slab) take in the two received messages, then re-sort
+int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_right) {
+    if (ctx->slab) {
+        const Buffers& b = ctx->buf[ctx->cur];
+        IncomingArgs a{msg(ctx, in_left), msg(ctx, in_right), b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count,
+                       ctx->cell_start, ctx->n_unsorted, ctx->err, ctx->cap, ctx->g};
+        ingest_incoming_kernel<<<std::max(1, std::min(1024, cdiv(2 * (ctx->cap_m + ctx->cap_g), 256))), 256, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
+    return rebuild(ctx);
+}
+
+// the exchange the library drives itself: a lone slab is its own neighbour on both sides; several slabs use NCCL
+int exchange(fishabm_ctx* ctx, unsigned char** in_left, unsigned char** in_right) {
+    if (ctx->p.nranks == 1) { *in_left = ctx->out_right; *in_right = ctx->out_left; return 0; }
+    if (!ctx->comm) return fail(ctx, FISHABM_E_STATE, "slab context is not connected: call fishabm_slab_connect, or drive the exchange with fishabm_slab_begin_step / end_step");
+    NcclApi& N = nccl();
+    NK(N.GroupStart());
+    NK(N.Send(ctx->out_left, ctx->msg_bytes, NCCL_UINT8, ctx->left, ctx->comm, ctx->stream));
+    NK(N.Send(ctx->out_right, ctx->msg_bytes, NCCL_UINT8, ctx->right, ctx->comm, ctx->stream));
+    // with two ranks both neighbours are the same peer: its first message (out_left) is what crosses MY right edge
+    NK(N.Recv(ctx->in_right, ctx->msg_bytes, NCCL_UINT8, ctx->right, ctx->comm, ctx->stream));
+    NK(N.Recv(ctx->in_left, ctx->msg_bytes, NCCL_UINT8, ctx->left, ctx->comm, ctx->stream));
+    NK(N.GroupEnd());
+    *in_left = ctx->in_left; *in_right = ctx->in_right;
+    return 0;
+}
+
+int update_pass(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
+    int rc = update_launch(ctx, do_sample, do_move, step_move);
+    if (rc || !do_move) return rc;
+    unsigned char *il = nullptr, *ir = nullptr;
+    if (ctx->slab && (rc = exchange(ctx, &il, &ir))) return rc;
+    return finish_move(ctx, il, ir);
 }
 
 int begin_timed(fishabm_ctx* ctx) {
@@ -174,16 +279,26 @@ int begin_timed(fishabm_ctx* ctx) {
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     return 0;
 }
+int check_device_errors(fishabm_ctx* ctx) {
+    if (!ctx->slab) return 0;
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (e & ERR_SLAB_OVERFLOW) return fail(ctx, FISHABM_E_NOMEM, "slab capacity exceeded (capacity %d, halo_capacity %d, migrant_capacity %d): raise fishabm_params.capacity / halo_capacity / migrant_capacity", ctx->cap, ctx->cap_g, ctx->cap_m);
+    if (e & ERR_STEP_TOO_LONG) return fail(ctx, FISHABM_E_ARG, "a fish moved more than 200 units in one step: not supported with slabs");
+    return 0;
+}
 int end_timed(fishabm_ctx* ctx) {
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    return 0;
+    return check_device_errors(ctx);
 }
 
 int need_state(fishabm_ctx* ctx) {
     if (!ctx) return FISHABM_E_ARG;
     if (!ctx->have_state) return fail(ctx, FISHABM_E_STATE, "no state: call fishabm_set_state or fishabm_initialize first");
+    if (ctx->step_open) return fail(ctx, FISHABM_E_STATE, "a slab step is open: call fishabm_slab_end_step first");
     return 0;
 }
 
@@ -195,6 +310,42 @@ int flush_pending(fishabm_ctx* ctx, bool timed = false) {
     if ((rc = neighbour_pass(ctx, 0, true, ctx->step - 1, ctx->step - 1, timed))) return rc;
     if ((rc = update_pass(ctx, true, false, ctx->step - 1))) return rc;
     ctx->pending_sample = false;
+    return 0;
+}
+
+// owned fish now (slab: read back from the device; whole school: n)
+int owned_range(fishabm_ctx* ctx, int* count) {
+    if (!ctx->slab) { *count = ctx->n; return 0; }
+    int be[2] = {0, 0};
+    CK(cudaMemcpyAsync(&be[0], ctx->cell_start + ctx->g.own_c0, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&be[1], ctx->cell_start + ctx->g.own_c1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *count = be[1] - be[0];
+    return 0;
+}
+
+// device staging -> the caller's array.  Whole school: the staging array is already in id order.  Slab: the
+// staging array is compact (owned fish in sorted order) and is scattered by id on the host.
+template <class T>
+int fetch(fishabm_ctx* ctx, T* user, const T* dev, int count, int width) {
+    if (!user) return 0;
+    if (!ctx->slab) {
+        CK(cudaMemcpyAsync(user, dev, (size_t)count * width * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+    }
+    ctx->h_tmp.resize((size_t)count * width * sizeof(T) + 1);
+    CK(cudaMemcpyAsync(ctx->h_tmp.data(), dev, (size_t)count * width * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const T* src = reinterpret_cast<const T*>(ctx->h_tmp.data());
+    for (int k = 0; k < count; ++k)
+        for (int c = 0; c < width; ++c) user[(size_t)ctx->h_ids[k] * width + c] = src[(size_t)k * width + c];
+    return 0;
+}
+int fetch_ids(fishabm_ctx* ctx, int count) {
+    if (!ctx->slab) return 0;
+    ctx->h_ids.resize((size_t)count + 1);
+    CK(cudaMemcpyAsync(ctx->h_ids.data(), ctx->st_ids, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -215,10 +366,11 @@ int fishabm_params_default(fishabm_params* p) {
     p->seed = 0;
     p->speed_norm = 0.0;
     p->rank = 0; p->nranks = 1; p->n_global = 0; p->capacity = 0;
+    p->halo_capacity = 0; p->migrant_capacity = 0; p->force_slab = 0;
     return 0;
 }
 
-const char* fishabm_last_error(const fishabm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* fishabm_last_error(const fishabm_ctx* ctx) { return ctx ? ctx->err_msg.c_str() : g_create_error.c_str(); }
 
 int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     fishabm_ctx* ctx = nullptr;  // for CK/fail before the context exists
@@ -229,8 +381,13 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (p->w % CELL_I || p->h % CELL_I || p->w < 3 * CELL_I || p->h < 3 * CELL_I)
         return fail(nullptr, FISHABM_E_ARG, "w and h must be multiples of 200 and at least 600 (got %d x %d)", p->w, p->h);
     if (p->mode != FISHABM_MODE_CELL_FP32) return fail(nullptr, FISHABM_E_ARG, "mode %d is not available in this build", p->mode);
-    if (p->replicates != 1) return fail(nullptr, FISHABM_E_ARG, "replicates > 1: use the ensemble entry points");
-    if (p->nranks != 1) return fail(nullptr, FISHABM_E_ARG, "nranks > 1: use the slab entry points");
+    if (p->replicates != 1) return fail(nullptr, FISHABM_E_ARG, "replicates > 1: use the ensemble entry points (fishabm_ensemble_*)");
+    if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(nullptr, FISHABM_E_ARG, "rank %d / nranks %d", p->rank, p->nranks);
+    // a fish that migrates into a slab's last column must not at the same time be a ghost for the slab beyond it
+    // (that slab's halo was packed before the migrant arrived): every slab needs two owned columns
+    if (p->nranks > 1 && 2 * p->nranks > p->w / CELL_I)
+        return fail(nullptr, FISHABM_E_ARG, "nranks %d: every slab needs at least 2 of the %d cell columns (w/200)", p->nranks, p->w / CELL_I);
+    if (p->n_global != 0 && p->n_global != p->n) return fail(nullptr, FISHABM_E_ARG, "n_global must be 0 or n: n is the size of the whole school on every rank");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1) return fail(nullptr, FISHABM_E_CUDA, "no CUDA device (%s): libfishabm has no CPU path", cudaGetErrorString(e));
@@ -242,32 +399,70 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (!c) return fail(nullptr, FISHABM_E_NOMEM, "out of host memory");
     c->p = *p;
     c->n = p->n;
-    c->nx = p->w / CELL_I; c->ny = p->h / CELL_I; c->ncell = c->nx * c->ny;
-    c->qrows = p->h / FOOD_I; c->qcols = p->w / FOOD_I;
+    const int nx_g = p->w / CELL_I, ny = p->h / CELL_I;
+    c->slab = p->nranks > 1 || p->force_slab;
+    c->col0 = (int)((long long)p->rank * nx_g / p->nranks);
+    const int col1 = (int)((long long)(p->rank + 1) * nx_g / p->nranks);
+    c->own = col1 - c->col0;
+    c->left = (p->rank + p->nranks - 1) % p->nranks;
+    c->right = (p->rank + 1) % p->nranks;
+    Grid& g = c->g;
+    g.ny = ny; g.nx_g = nx_g;
+    if (c->slab) {
+        g.lnx = c->own + 2; g.wrap_x = 0; g.gx0 = (c->col0 - 1 + nx_g) % nx_g;
+        g.own_c0 = ny; g.own_c1 = (g.lnx - 1) * ny;
+    } else {
+        g.lnx = nx_g; g.wrap_x = 1; g.gx0 = 0; g.own_c0 = 0; g.own_c1 = nx_g * ny;
+    }
+    g.ncell = g.lnx * ny;
+    c->ncell = g.ncell;
+    c->qrows = p->h / FOOD_I; c->qcols = c->own * FOOD_PER_CELL; c->qcols_g = p->w / FOOD_I; c->qcol0 = c->col0 * FOOD_PER_CELL;
     c->speed_norm = p->speed_norm > 0 ? p->speed_norm : (double)p->n;
-    const size_t n = (size_t)c->n, nq = (size_t)c->qrows * c->qcols;
+    if (c->slab) {
+        const double per_col = (double)p->n / nx_g;
+        c->cap_g = p->halo_capacity > 0 ? p->halo_capacity : (int)(2.0 * per_col) + 4096;
+        c->cap_m = p->migrant_capacity > 0 ? p->migrant_capacity : (int)(0.25 * per_col) + 2048;
+        const double want = p->capacity > 0 ? (double)p->capacity : 1.3 * per_col * (c->own + 4) + 16384.0;
+        if (want >= (double)(1 << 28)) { delete c; return fail(nullptr, FISHABM_E_ARG, "slab capacity must stay below 2^28 entries"); }
+        c->cap = (int)want;
+        c->msg_bytes = SlabMsg::bytes(c->cap_m, c->cap_g);
+    } else {
+        c->cap = p->n;
+    }
+    const size_t n = (size_t)c->n, cap = (size_t)c->cap, nq = (size_t)c->qrows * c->qcols;
     bool ok = true;
-    auto A = [&](cudaError_t r) { if (r != cudaSuccess) { ok = false; g_create_error = cudaGetErrorString(r); } };
+    auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; g_create_error = cudaGetErrorString(r); } };
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
     for (int k = 0; k < 2 && ok; ++k) {
-        A(dalloc(&c->buf[k].rec, n)); A(dalloc(&c->buf[k].cold0, n)); A(dalloc(&c->buf[k].cold1, n)); A(dalloc(&c->buf[k].cell, n));
+        A(dalloc(&c->buf[k].rec, cap)); A(dalloc(&c->buf[k].cold0, cap)); A(dalloc(&c->buf[k].cold1, cap)); A(dalloc(&c->buf[k].cell, cap));
     }
-    A(dalloc(&c->next_cell, n)); A(dalloc(&c->next_rank, n));
+    A(dalloc(&c->next_cell, cap)); A(dalloc(&c->next_rank, cap));
     A(dalloc(&c->cell_count, (size_t)c->ncell + 1)); A(dalloc(&c->cell_start, (size_t)c->ncell + 1));
     A(dalloc(&c->tile_sums, (size_t)cdiv(c->ncell, SCAN_TILE) + 1));
-    A(dalloc(&c->cnt, n)); A(dalloc(&c->turn, n)); A(dalloc(&c->aux, n));
+    A(dalloc(&c->cnt, cap)); A(dalloc(&c->turn, cap)); A(dalloc(&c->aux, cap));
     A(dalloc(&c->quality, nq));
-    A(dalloc(&c->upd_count, 1)); A(dalloc(&c->upd_idx, n)); A(dalloc(&c->upd_val, n));
+    A(dalloc(&c->upd_count, 1)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
     A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 1)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
+    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
-    A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n));
+    A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
+    if (c->slab) {
+        A(dalloc(&c->out_left, c->msg_bytes)); A(dalloc(&c->out_right, c->msg_bytes));
+        A(dalloc(&c->in_left, c->msg_bytes)); A(dalloc(&c->in_right, c->msg_bytes));
+    }
     if (ok) {
         A(cudaMemset(c->cell_count, 0, ((size_t)c->ncell + 1) * sizeof(int)));
+        A(cudaMemset(c->cell_start, 0, ((size_t)c->ncell + 1) * sizeof(int)));
         A(cudaMemset(c->quality, 0, nq));
         A(cudaMemset(c->upd_count, 0, sizeof(int)));
+        A(cudaMemset(c->err, 0, sizeof(int)));
         A(cudaMemset(c->stats, 0, 8 * sizeof(unsigned long long)));
-        A(cudaMemset(c->aux, 0, n * sizeof(uint32_t)));
+        A(cudaMemset(c->aux, 0, cap * sizeof(uint32_t)));
+        if (c->slab) {
+            A(cudaMemset(c->out_left, 0, sizeof(SlabHeader))); A(cudaMemset(c->out_right, 0, sizeof(SlabHeader)));
+            A(cudaMemset(c->in_left, 0, sizeof(SlabHeader))); A(cudaMemset(c->in_right, 0, sizeof(SlabHeader)));
+        }
     }
     if (ok) {
         A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
@@ -296,12 +491,15 @@ void fishabm_destroy(fishabm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
     for (int k = 0; k < 2; ++k) { cudaFree(c->buf[k].rec); cudaFree(c->buf[k].cold0); cudaFree(c->buf[k].cold1); cudaFree(c->buf[k].cell); }
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
+    cudaFree(c->n_unsorted); cudaFree(c->err);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
-    cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4);
+    cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
+    cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);
     for (auto& pr : c->nb_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -314,11 +512,16 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
                       const int32_t* lag, const int32_t* sample_rate, const int32_t* food_intake) {
     if (!ctx || !coords || !dir || !speed || !speed_factor || !lag || !sample_rate || !food_intake)
         return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: null argument");
+    if (ctx->step_open) return fail(ctx, FISHABM_E_STATE, "a slab step is open: call fishabm_slab_end_step first");
     CK(cudaSetDevice(ctx->p.device));
     if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     ctx->pending_sample = false;
     const size_t n = (size_t)ctx->n;
     cudaStream_t s = ctx->stream;
+    if (ctx->slab) {  // a fish may not outrun its halo: |step| = speed * speed_factor <= 3 * speed must stay below one cell
+        for (size_t i = 0; i < n; ++i)
+            if (!(speed[i] * 3.0 < (double)CELL_I)) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: speed %g of fish %zu: slabs need 3*speed < 200", speed[i], i);
+    }
     CK(cudaMemcpyAsync(ctx->st_coords, coords, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_dir, dir, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_speed, speed, n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -327,11 +530,14 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     CK(cudaMemcpyAsync(ctx->st_rate, sample_rate, n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_intake, food_intake, n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->err, 0, sizeof(int), s));
     CK(cudaMemsetAsync(ctx->cell_count, 0, ((size_t)ctx->ncell + 1) * sizeof(int), s));
+    ctx->h_n = ctx->slab ? 0 : ctx->n;  // whole school: entry i = fish i; slab: entries are claimed
+    CK(cudaMemcpyAsync(ctx->n_unsorted, &ctx->h_n, sizeof(int), cudaMemcpyHostToDevice, s));
     const Buffers& b = ctx->buf[ctx->cur];
     IngestArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake,
-                 b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count,
-                 ctx->n, ctx->nx, ctx->ny, 0, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+                 b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted,
+                 ctx->n, ctx->cap, ctx->g, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
     ingest_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     int rc = rebuild(ctx);
@@ -339,7 +545,8 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->bad, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (bad) { ctx->have_state = false; return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: coordinates must be finite and inside [0,w] x [0,h]"); }
+    if (bad & 1) { ctx->have_state = false; return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: coordinates must be finite and inside [0,w] x [0,h]"); }
+    if (bad & 2) { ctx->have_state = false; return fail(ctx, FISHABM_E_NOMEM, "fishabm_set_state: this slab holds more than its capacity of %d entries: raise fishabm_params.capacity", ctx->cap); }
     ctx->have_state = true;
     return 0;
 }
@@ -350,23 +557,25 @@ int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* spe
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
-    const size_t n = (size_t)ctx->n;
+    int cnt = 0;
+    if ((rc = owned_range(ctx, &cnt))) return rc;
     cudaStream_t s = ctx->stream;
     const Buffers& b = ctx->buf[ctx->cur];
-    ExportArgs a{b.rec, b.cold0, b.cold1, b.cell,
+    ExportArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start,
                  coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr, speed ? ctx->st_speed : nullptr,
                  speed_factor ? ctx->st_sf : nullptr, lag ? ctx->st_lag : nullptr, sample_rate ? ctx->st_rate : nullptr,
-                 food_intake ? ctx->st_intake : nullptr, ctx->n, ctx->nx, 0};
-    export_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(a);
+                 food_intake ? ctx->st_intake : nullptr, ctx->slab ? ctx->st_ids : nullptr, ctx->g, ctx->slab ? 1 : 0};
+    if (cnt > 0) export_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (speed) CK(cudaMemcpyAsync(speed, ctx->st_speed, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (speed_factor) CK(cudaMemcpyAsync(speed_factor, ctx->st_sf, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (lag) CK(cudaMemcpyAsync(lag, ctx->st_lag, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (sample_rate) CK(cudaMemcpyAsync(sample_rate, ctx->st_rate, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (food_intake) CK(cudaMemcpyAsync(food_intake, ctx->st_intake, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if ((rc = fetch_ids(ctx, cnt))) return rc;
+    if ((rc = fetch(ctx, coords, ctx->st_coords, cnt, 2))) return rc;
+    if ((rc = fetch(ctx, dir, ctx->st_dir, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, speed, ctx->st_speed, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, speed_factor, ctx->st_sf, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, lag, ctx->st_lag, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, sample_rate, ctx->st_rate, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, food_intake, ctx->st_intake, cnt, 1))) return rc;
     CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -386,33 +595,34 @@ int fishabm_initialize(fishabm_ctx* ctx, double speed) {
     return fishabm_set_state(ctx, coords.data(), dir.data(), sp.data(), sf.data(), z.data(), z.data(), z.data());
 }
 
+// the food grid arguments are the WHOLE grid (h/20 x w/20); a slab keeps / returns its owned columns
 int fishabm_set_quality(fishabm_ctx* ctx, const int32_t* q, int32_t rows, int32_t cols, int32_t row_stride) {
     if (!ctx || !q) return fail(ctx, FISHABM_E_ARG, "fishabm_set_quality: null argument");
-    if (rows != ctx->qrows || cols != ctx->qcols || row_stride < cols)
-        return fail(ctx, FISHABM_E_ARG, "fishabm_set_quality: grid must be %d x %d (h/20 x w/20), got %d x %d", ctx->qrows, ctx->qcols, rows, cols);
+    if (rows != ctx->qrows || cols != ctx->qcols_g || row_stride < cols)
+        return fail(ctx, FISHABM_E_ARG, "fishabm_set_quality: grid must be %d x %d (h/20 x w/20), got %d x %d", ctx->qrows, ctx->qcols_g, rows, cols);
     for (int r = 0; r < rows; ++r)
-        for (int c = 0; c < cols; ++c) {
-            const int v = q[(size_t)r * row_stride + c];
-            if (v < 0 || v > 255) return fail(ctx, FISHABM_E_ARG, "fishabm_set_quality: value %d at (%d,%d) outside 0..255", v, r, c);
-            ctx->h_q8[(size_t)r * cols + c] = (uint8_t)v;
+        for (int c = 0; c < ctx->qcols; ++c) {
+            const int v = q[(size_t)r * row_stride + ctx->qcol0 + c];
+            if (v < 0 || v > 255) return fail(ctx, FISHABM_E_ARG, "fishabm_set_quality: value %d at (%d,%d) outside 0..255", v, r, ctx->qcol0 + c);
+            ctx->h_q8[(size_t)r * ctx->qcols + c] = (uint8_t)v;
         }
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
-    CK(cudaMemcpyAsync(ctx->quality, ctx->h_q8, (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->quality, ctx->h_q8, (size_t)rows * ctx->qcols, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 int fishabm_get_quality(fishabm_ctx* ctx, int32_t replicate, int32_t* q, int32_t rows, int32_t cols, int32_t row_stride) {
     if (!ctx || !q) return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: null argument");
-    if (replicate != 0 || rows != ctx->qrows || cols != ctx->qcols || row_stride < cols)
-        return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: grid is %d x %d, replicate 0", ctx->qrows, ctx->qcols);
+    if (replicate != 0 || rows != ctx->qrows || cols != ctx->qcols_g || row_stride < cols)
+        return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: grid is %d x %d, replicate 0", ctx->qrows, ctx->qcols_g);
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
-    CK(cudaMemcpyAsync(ctx->h_q8, ctx->quality, (size_t)rows * cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_q8, ctx->quality, (size_t)rows * ctx->qcols, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < rows; ++r)
-        for (int c = 0; c < cols; ++c) q[(size_t)r * row_stride + c] = ctx->h_q8[(size_t)r * cols + c];
+        for (int c = 0; c < ctx->qcols; ++c) q[(size_t)r * row_stride + ctx->qcol0 + c] = ctx->h_q8[(size_t)r * ctx->qcols + c];
     return 0;
 }
 
@@ -469,22 +679,24 @@ int fishabm_load_quality_csv(const char* path, int32_t* q, int32_t max_rows, int
 
 // ---- frozen-state queries ------------------------------------------------------------------------------
 static int export_pass(fishabm_ctx* ctx, int32_t* cnt4, double* turn, int32_t* n_avoid, int32_t* n_align, int32_t* n_attract, double* speed) {
-    const size_t n = (size_t)ctx->n;
+    int rc, cnt = 0;
+    if ((rc = owned_range(ctx, &cnt))) return rc;
     cudaStream_t s = ctx->stream;
     int* d4 = ctx->st_i4;
-    ExportPassArgs a{ctx->buf[ctx->cur].cold1, ctx->cnt, ctx->turn, ctx->aux,
+    ExportPassArgs a{ctx->buf[ctx->cur].cold1, ctx->cnt, ctx->turn, ctx->aux, ctx->cell_start,
                      cnt4 ? d4 : nullptr, turn ? ctx->st_dir : nullptr, n_avoid ? ctx->st_lag : nullptr,
                      n_align ? ctx->st_rate : nullptr, n_attract ? ctx->st_intake : nullptr, speed ? ctx->st_sf : nullptr,
-                     ctx->n, 0, ctx->speed_norm};
-    export_pass_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(a);
+                     ctx->slab ? ctx->st_ids : nullptr, ctx->g, ctx->slab ? 1 : 0, ctx->speed_norm};
+    if (cnt > 0) export_pass_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    if (cnt4) CK(cudaMemcpyAsync(cnt4, d4, 4 * n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (turn) CK(cudaMemcpyAsync(turn, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (n_avoid) CK(cudaMemcpyAsync(n_avoid, ctx->st_lag, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (n_align) CK(cudaMemcpyAsync(n_align, ctx->st_rate, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (n_attract) CK(cudaMemcpyAsync(n_attract, ctx->st_intake, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (speed) CK(cudaMemcpyAsync(speed, ctx->st_sf, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if ((rc = fetch_ids(ctx, cnt))) return rc;
+    if ((rc = fetch(ctx, cnt4, d4, cnt, 4))) return rc;
+    if ((rc = fetch(ctx, turn, ctx->st_dir, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, n_avoid, ctx->st_lag, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, n_align, ctx->st_rate, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, n_attract, ctx->st_intake, cnt, 1))) return rc;
+    if ((rc = fetch(ctx, speed, ctx->st_sf, cnt, 1))) return rc;
     CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -526,12 +738,15 @@ int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out) {
     if (!(r <= 200.0) || fov_deg < 0 || fov_deg > 360) return fail(ctx, FISHABM_E_ARG, "fishabm_in_zone: needs r <= 200 and 0 <= fov <= 360");
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    int cnt = 0;
+    if ((rc = owned_range(ctx, &cnt))) return rc;
     const Buffers& b = ctx->buf[ctx->cur];
-    ZoneArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start, ctx->st_lag, ctx->n, ctx->nx, ctx->ny, 0, fov_deg / 2, r};
-    in_zone_generic_kernel<<<cdiv(ctx->n, 128), 128, 0, ctx->stream>>>(a);
+    ZoneArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start, ctx->st_lag, ctx->slab ? ctx->st_ids : nullptr, ctx->g, ctx->slab ? 1 : 0, fov_deg / 2, r};
+    if (cnt > 0) in_zone_generic_kernel<<<cdiv(cnt, 128), 128, 0, ctx->stream>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, ctx->st_lag, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = fetch_ids(ctx, cnt))) return rc;
+    if ((rc = fetch(ctx, out, ctx->st_lag, cnt, 1))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -563,20 +778,28 @@ int fishabm_sample(fishabm_ctx* ctx) {
     return end_timed(ctx);
 }
 
+// first half of one step: the neighbour pass and the per-fish update, up to the packed slab messages
+static int step_first_half(fishabm_ctx* ctx) {
+    int rc;
+    const uint32_t s = ctx->step;
+    if (ctx->pending_sample) {  // sample(s-1) and move(s) share one neighbour pass
+        if ((rc = neighbour_pass(ctx, 1, true, s - 1, s, true))) return rc;
+        return update_launch(ctx, true, true, s);
+    }
+    if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
+    return update_launch(ctx, false, true, s);
+}
+
 static int step_untimed(fishabm_ctx* ctx, int nsteps) {
     // move(s); { sample(s+t-1) + move(s+t) } ...; the trailing sample stays pending (flush_pending)
     int rc;
     for (int t = 0; t < nsteps; ++t) {
-        const uint32_t s = ctx->step;
-        if (ctx->pending_sample) {
-            if ((rc = neighbour_pass(ctx, 1, true, s - 1, s, true))) return rc;
-            if ((rc = update_pass(ctx, true, true, s))) return rc;
-        } else {
-            if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
-            if ((rc = update_pass(ctx, false, true, s))) return rc;
-        }
+        if ((rc = step_first_half(ctx))) return rc;
+        unsigned char *il = nullptr, *ir = nullptr;
+        if (ctx->slab && (rc = exchange(ctx, &il, &ir))) return rc;
+        if ((rc = finish_move(ctx, il, ir))) return rc;
         ctx->pending_sample = true;
-        ctx->step = s + 1;
+        ctx->step += 1;
     }
     return 0;
 }
@@ -616,7 +839,7 @@ int fishabm_run_logged(fishabm_ctx* ctx, int32_t nsteps, int64_t* sumq, int32_t*
         if (sumq && (rc = fishabm_sum_quality(ctx, sumq + z))) return rc;
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return check_device_errors(ctx);
 }
 
 int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k) {
@@ -629,12 +852,97 @@ int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k) {
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     const Buffers& b = ctx->buf[ctx->cur];
     CK(cudaMemcpyAsync(ctx->st_lag, ids, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    index_by_id_kernel<<<cdiv(ctx->n, 256), 256, 0, ctx->stream>>>(b.cold1, ctx->n, 0, ctx->pos_of_id);
-    FeedArgs a{b.cold0, b.cold1, b.rec, b.cell, ctx->st_lag, k, ctx->quality, ctx->n, ctx->nx, ctx->qcols, 0, ctx->pos_of_id};
+    CK(cudaMemsetAsync(ctx->pos_of_id, 0xFF, (size_t)ctx->n * sizeof(int), ctx->stream));
+    index_by_id_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(b.cold1, ctx->cell_start, ctx->g, ctx->pos_of_id);
+    FeedArgs a{b.cold0, b.cold1, b.rec, b.cell, ctx->st_lag, k, ctx->quality, ctx->n, ctx->qcols, ctx->g, ctx->pos_of_id};
     feed_list_kernel<<<1, 32, 0, ctx->stream>>>(a);
     ctx->launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- slab decomposition ------------------------------------------------------------------------------------
+int fishabm_slab_get_info(fishabm_ctx* ctx, fishabm_slab_info* out) {
+    if (!ctx || !out) return FISHABM_E_ARG;
+    memset(out, 0, sizeof *out);
+    out->rank = ctx->p.rank; out->nranks = ctx->p.nranks; out->left = ctx->left; out->right = ctx->right;
+    out->col0 = ctx->col0; out->col1 = ctx->col0 + ctx->own;
+    out->capacity = ctx->cap; out->halo_capacity = ctx->cap_g; out->migrant_capacity = ctx->cap_m;
+    out->message_bytes = (int64_t)ctx->msg_bytes;
+    if (ctx->have_state) {
+        CK(cudaSetDevice(ctx->p.device));
+        int own = 0, held = 0, rc;
+        if ((rc = owned_range(ctx, &own))) return rc;
+        CK(cudaMemcpyAsync(&held, ctx->cell_start + ctx->ncell, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out->owned = own; out->held = held;
+    }
+    return 0;
+}
+
+int fishabm_slab_unique_id(void* id_out, int32_t bytes) {
+    fishabm_ctx* ctx = nullptr;
+    if (!id_out || bytes < FISHABM_UNIQUE_ID_BYTES) return fail(nullptr, FISHABM_E_ARG, "fishabm_slab_unique_id: needs a %d-byte buffer", FISHABM_UNIQUE_ID_BYTES);
+    NcclApi& N = nccl();
+    if (!N.h) return fail(nullptr, FISHABM_E_COMM, "%s", N.why.c_str());
+    NcclUniqueId id;
+    NK(N.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int fishabm_slab_connect(fishabm_ctx* ctx, const void* id, int32_t bytes) {
+    if (!ctx || !id || bytes < FISHABM_UNIQUE_ID_BYTES) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_connect: bad argument");
+    if (!ctx->slab || ctx->p.nranks < 2) return fail(ctx, FISHABM_E_STATE, "fishabm_slab_connect: the context is not one of several slabs");
+    if (ctx->comm) return fail(ctx, FISHABM_E_STATE, "fishabm_slab_connect: already connected");
+    NcclApi& N = nccl();
+    if (!N.h) return fail(ctx, FISHABM_E_COMM, "%s", N.why.c_str());
+    CK(cudaSetDevice(ctx->p.device));
+    NcclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NK(N.CommInitRank(&ctx->comm, ctx->p.nranks, uid, ctx->p.rank));
+    return 0;
+}
+
+int fishabm_slab_begin_step(fishabm_ctx* ctx) {
+    int rc = need_state(ctx);
+    if (rc) return rc;
+    if (!ctx->slab) return fail(ctx, FISHABM_E_STATE, "not a slab context");
+    CK(cudaSetDevice(ctx->p.device));
+    ctx->nb_events_used = 0;
+    if ((rc = step_first_half(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->step_open = true;
+    return 0;
+}
+
+int fishabm_slab_buffers(fishabm_ctx* ctx, void** out_left, void** out_right, void** in_left, void** in_right, int64_t* bytes) {
+    if (!ctx || !ctx->slab) return fail(ctx, FISHABM_E_STATE, "not a slab context");
+    if (out_left) *out_left = ctx->out_left;
+    if (out_right) *out_right = ctx->out_right;
+    if (in_left) *in_left = ctx->in_left;
+    if (in_right) *in_right = ctx->in_right;
+    if (bytes) *bytes = (int64_t)ctx->msg_bytes;
+    return 0;
+}
+
+int fishabm_slab_end_step(fishabm_ctx* ctx) {
+    if (!ctx || !ctx->slab || !ctx->step_open) return fail(ctx, FISHABM_E_STATE, "fishabm_slab_end_step without fishabm_slab_begin_step");
+    CK(cudaSetDevice(ctx->p.device));
+    int rc = finish_move(ctx, ctx->in_left, ctx->in_right);
+    if (rc) return rc;
+    ctx->step_open = false;
+    ctx->pending_sample = true;
+    ctx->step += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return check_device_errors(ctx);
+}
+
+int fishabm_slab_copy(void* dst, const void* src, int64_t bytes) {
+    if (!dst || !src || bytes < 0) return FISHABM_E_ARG;
+    if (cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault) != cudaSuccess) return FISHABM_E_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return FISHABM_E_CUDA;  // device-to-device copies return early
     return 0;
 }
 

@@ -5,8 +5,12 @@
 //                                                cell (ulp <= 1.5e-5 at any world size) + heading unit vector
 //   cold0 float4 {dir_deg (unwrapped), speed, speed_factor, unused}
 //   cold1 int4   {lag, sample_rate, food_intake, global id}
-//   cell  int    cell index (cy*nx+cx) of the fish
-//   cell_start[ncell+1]                          exclusive scan of the per-cell counts
+//   cell  int    LOCAL cell index of the fish, column-major: c = lcx*ny + cy, so that a cell COLUMN is one
+//                contiguous slice of every sorted array (a slab's boundary column needs no gather)
+//   cell_start[ncell+1]                          exclusive scan of the per-cell counts; cell_start[ncell] = fish held
+// One context holds `lnx` local columns of `ny` cells.  A whole school: lnx = W/200, periodic in x.  One slab of a
+// school split across GPUs (nranks > 1): lnx = owned columns + 2, local columns 0 and lnx-1 are HALO columns whose
+// fish (ghosts) are candidates only; x is not periodic locally (the halo is), y always is.
 // Per-pass outputs (sorted order): cnt int4 {n15, n100, n200, front}, turn float (deg), aux uint32.
 //
 // Kernels:
@@ -18,6 +22,7 @@
 //                                       random walk, and sample()'s feeding decision
 //   K5 update_kernel                  - sample()/feed()/move() state transition per fish
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -45,6 +50,15 @@ constexpr int FIX_SHIFT = 20;            // fixed-point fraction bits of the cos
 constexpr float FIX_MAGIC = 12.0f;       // x + 12.0f has ulp 2^-20 for x in [-1,1]
 constexpr int FIX_MAGIC_BITS = 0x41400000;
 
+// local grid of one context
+struct Grid {
+    int lnx, ny, ncell;    // local columns (halos included), rows, lnx*ny
+    int own_c0, own_c1;    // owned cells [own_c0, own_c1): whole school [0,ncell); slab [ny, (lnx-1)*ny)
+    int wrap_x;            // 1 = periodic in x locally (whole school); 0 = slab with halo columns
+    int gx0;               // global column of local column 0
+    int nx_g;              // global columns (W/200)
+};
+
 struct NeighArgs {
     const float4* rec;
     const float4* cold0;
@@ -54,7 +68,7 @@ struct NeighArgs {
     float* turn;
     uint32_t* aux;
     unsigned long long* stats;   // [4] focal, candidates, interacting, rechecked (may be null)
-    int ncell, nx, ny;
+    Grid g;
     int active_lag_max;          // fish with lag > this are skipped (their outputs are not needed); <0: all fish
     int do_sample;               // evaluate sample()'s feeding decision into aux
     uint32_t step_sample, step_move;
@@ -126,6 +140,15 @@ __device__ __noinline__ float getangle_wrap_exotic(float beta_rad, float dir_raw
     if (a < 0) a += 360.0; else if (a >= 360.0) a -= 360.0;
     if (a > 180.0) a -= 360.0;
     return (float)(a * (M_PI / 180.0));
+}
+
+// cell k (0..8) of the 3x3 stencil around cell c: x offset k%3-1, y offset k/3-1.  Owned cells of a slab always
+// have both x neighbours inside the local grid (the halo columns).
+__device__ __forceinline__ int stencil_cell(const Grid& g, int c, int k) {
+    int xx = c / g.ny + (k % 3) - 1, yy = c % g.ny + (k / 3) - 1;
+    if (g.wrap_x) xx = xx < 0 ? xx + g.lnx : (xx >= g.lnx ? xx - g.lnx : xx);
+    yy = yy < 0 ? yy + g.ny : (yy >= g.ny ? yy - g.ny : yy);
+    return xx * g.ny + yy;
 }
 
 struct FocalAcc {
@@ -269,17 +292,13 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
     __shared__ uint32_t s_tj[NB_WARPS * NB_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
-    const int c = blockIdx.x * NB_WARPS + warp;
-    if (c >= a.ncell) return;
+    const int c = a.g.own_c0 + blockIdx.x * NB_WARPS + warp;
+    if (c >= a.g.own_c1) return;
     const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
     if (s0 == e0) return;
-    const int cx = c % a.nx, cy = c / a.nx;
     int nb_s = 0, nb_e = 0;
     if (lane < 9) {
-        int xx = cx + (lane % 3) - 1, yy = cy + (lane / 3) - 1;
-        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
-        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
-        const int cc = yy * a.nx + xx;
+        const int cc = stencil_cell(a.g, c, lane);
         nb_s = a.cell_start[cc];
         nb_e = a.cell_start[cc + 1];
     }
@@ -349,6 +368,45 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Slab messages (nranks > 1): what one slab sends to ONE neighbour after its fish have moved.
+//   migrants: fish that crossed into the neighbour's first/last owned column (full state)
+//   ghosts  : the fish now in this slab's own boundary column (hot record + id), the neighbour's next halo
+// Fixed capacity, counts in the header, so that the exchange needs no host round trip.
+// ------------------------------------------------------------------------------------------------------
+struct SlabHeader { int n_mig, n_ghost, overflow, pad; };
+struct MigRec { float4 rec; float4 cold0; int4 cold1; int cy; int pad[3]; };
+struct GhostRec { float4 rec; int id; int cy; int pad[2]; };
+
+struct SlabMsg {  // view of one message buffer
+    unsigned char* base;
+    int cap_m, cap_g;
+    __host__ __device__ SlabHeader* hdr() const { return reinterpret_cast<SlabHeader*>(base); }
+    __host__ __device__ MigRec* mig() const { return reinterpret_cast<MigRec*>(base + sizeof(SlabHeader)); }
+    __host__ __device__ GhostRec* ghost() const { return reinterpret_cast<GhostRec*>(base + sizeof(SlabHeader) + (size_t)cap_m * sizeof(MigRec)); }
+    __host__ __device__ static size_t bytes(int cap_m, int cap_g) { return sizeof(SlabHeader) + (size_t)cap_m * sizeof(MigRec) + (size_t)cap_g * sizeof(GhostRec); }
+};
+
+// slot claim with one atomic per converged warp (the fish of a boundary column are contiguous in sorted order, so
+// whole warps arrive here together)
+__device__ __forceinline__ int claim_slot(int* counter) {
+    const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, (int)g.size());
+    return g.shfl(base, 0) + (int)g.thread_rank();
+}
+
+__device__ __forceinline__ void slab_push_migrant(const SlabMsg& m, const float4& r, const float4& c0, const int4& c1, int cy) {
+    const int k = claim_slot(&m.hdr()->n_mig);
+    if (k < m.cap_m) { MigRec& o = m.mig()[k]; o.rec = r; o.cold0 = c0; o.cold1 = c1; o.cy = cy; }
+    else m.hdr()->overflow = 1;
+}
+__device__ __forceinline__ void slab_push_ghost(const SlabMsg& m, const float4& r, int id, int cy) {
+    const int k = claim_slot(&m.hdr()->n_ghost);
+    if (k < m.cap_g) { GhostRec& o = m.ghost()[k]; o.rec = r; o.id = id; o.cy = cy; }
+    else m.hdr()->overflow = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K5: per-fish state transition
 // ------------------------------------------------------------------------------------------------------
 struct UpdateArgs {
@@ -360,28 +418,40 @@ struct UpdateArgs {
     const int4* cnt;
     const float* turn;
     const uint32_t* aux;
-    int* next_cell;     // out: cell after the move
+    int* next_cell;     // out: cell after the move (-1: entry dropped by the next sort)
     int* next_rank;     // out: rank claimed in that cell
     int* next_count;    // per-cell counters being built for the next sort (atomic)
-    uint8_t* quality;   // food grid, rows x cols
+    uint8_t* quality;   // food grid of the owned columns, rows x qcols
     int* upd_count;     // deferred food-grid updates (applied after this kernel)
     int* upd_idx;
     uint8_t* upd_val;
-    int n, nx, ny, qcols;
+    int* err;           // sticky error flags (ERR_*)
+    Grid g;
+    int qcols;
     int do_sample, do_move, rolling;
     uint32_t step_move;
     uint64_t seed;
     uint32_t replicate;
     double speed_norm;
+    int slab;           // pack migrants / ghosts for the two neighbours
+    SlabMsg out_left, out_right;
 };
+
+constexpr int ERR_SLAB_OVERFLOW = 1;   // a slab message or the fish arrays overflowed their capacity
+constexpr int ERR_STEP_TOO_LONG = 2;   // a fish moved further than one neighbour cell in one step (slab mode)
 
 __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= a.cell_start[a.g.ncell]) return;
+    if (i < a.cell_start[a.g.own_c0] || i >= a.cell_start[a.g.own_c1]) {  // ghost: rebuilt by every exchange
+        if (a.do_move) a.next_cell[i] = -1;
+        return;
+    }
     float4 c0 = a.cold0[i];
     int4 c1 = a.cold1[i];
     const int mycell = a.cell[i];
     const uint32_t aux = a.do_sample ? a.aux[i] : 0u;
+    const int ny = a.g.ny;
 
     if (a.do_sample) {  // sample(), fish_mod.cpp:546-556
         if (aux & AUX_WANTS) {
@@ -399,8 +469,8 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
                 }
             }
             const int fl = (int)((aux >> AUX_FOOD_SHIFT) & AUX_FOOD_MASK);
-            const int gx = (mycell % a.nx) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
-            const int gy = (mycell / a.nx) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
+            const int gx = (mycell / ny - a.g.own_c0 / ny) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
+            const int gy = (mycell % ny) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
             const int qi = gy * a.qcols + gx;
             const int q = (int)a.quality[qi];
             if (rank < q) { c0.z = 0.5f; c1.z += 1; c1.y = 30; }
@@ -414,11 +484,11 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
         else c1.x -= 1;
     }
 
-    int newcell = mycell;
     if (a.do_move) {  // move(), fish_mod.cpp:165-179
         const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -10, 10);
         float4 r = a.rec[i];
         double dir = (double)c0.x;
+        int cx = mycell / ny, cy = mycell % ny;
         if (c1.x == 0) {
             double d0 = dir;
             if (d0 < 0) d0 += 360.0; else if (d0 >= 360.0) d0 -= 360.0;  // correctangle, :410-418
@@ -429,15 +499,14 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
             double px = (double)r.x + stepl * cs, py = (double)r.y + stepl * sn;
             if (a.rolling) c0.z = (float)(1.0 + 2.0 * (double)a.cnt[i].w / a.speed_norm);  // get_speed, :588-591
             // periodic wrap (correct_coords, :466-480) in cell/offset form
-            int cx = mycell % a.nx, cy = mycell / a.nx;
             const double kx = floor(px / (double)CELL_I), ky = floor(py / (double)CELL_I);
             float ox = (float)(px - kx * CELL_I), oy = (float)(py - ky * CELL_I);
             cx += (int)kx; cy += (int)ky;
             if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
             if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
-            cx %= a.nx; if (cx < 0) cx += a.nx;
-            cy %= a.ny; if (cy < 0) cy += a.ny;
-            newcell = cy * a.nx + cx;
+            if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
+            else if (cx < 0 || cx >= a.g.lnx) { atomicOr(a.err, ERR_STEP_TOO_LONG); cx = max(0, min(cx, a.g.lnx - 1)); }
+            cy %= ny; if (cy < 0) cy += ny;
             r.x = ox; r.y = oy;
         } else {
             dir = dir + (double)err;  // :177-179
@@ -446,9 +515,18 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
         double sn, cs;
         sincospi((double)c0.x / 180.0, &sn, &cs);
         r.z = (float)cs; r.w = (float)sn;
+        const int newcell = cx * ny + cy;
         a.rec[i] = r;
         a.next_cell[i] = newcell;
         a.next_rank[i] = atomicAdd(&a.next_count[newcell], 1);
+        if (a.slab) {
+            // crossing into a halo column = leaving the slab: the full state goes to that neighbour (the local
+            // copy stays behind as next step's ghost); standing in a boundary column = being the neighbour's ghost
+            if (cx == 0) slab_push_migrant(a.out_left, r, c0, c1, cy);
+            if (cx == a.g.lnx - 1) slab_push_migrant(a.out_right, r, c0, c1, cy);
+            if (cx == 1) slab_push_ghost(a.out_left, r, c1.w, cy);
+            if (cx == a.g.lnx - 2) slab_push_ghost(a.out_right, r, c1.w, cy);
+        }
     }
     a.cold0[i] = c0;
     a.cold1[i] = c1;
@@ -460,6 +538,50 @@ __global__ void apply_quality_updates_kernel(uint8_t* quality, int* upd_count, c
 }
 __global__ void reset_counter_kernel(int* p) { *p = 0; }
 
+// After the exchange: the two received messages become unsorted entries behind the fish already held
+// (left neighbour's migrants -> my first owned column, its ghosts -> my left halo; mirrored for the right).
+struct IncomingArgs {
+    SlabMsg in_left, in_right;
+    float4* rec; float4* cold0; int4* cold1;
+    int* next_cell; int* next_rank; int* next_count;
+    const int* cell_start;   // cell_start[ncell] = entries held before the exchange
+    int* n_unsorted;         // out: entries the scatter has to look at
+    int* err;
+    int cap_total;
+    Grid g;
+};
+__global__ void __launch_bounds__(256) ingest_incoming_kernel(const IncomingArgs a) {
+    const SlabHeader hl = *a.in_left.hdr(), hr = *a.in_right.hdr();
+    const int lm = min(hl.n_mig, a.in_left.cap_m), lg = min(hl.n_ghost, a.in_left.cap_g);
+    const int rm = min(hr.n_mig, a.in_right.cap_m), rg = min(hr.n_ghost, a.in_right.cap_g);
+    const int base = a.cell_start[a.g.ncell];
+    const int total = lm + lg + rm + rg;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.n_unsorted = min(base + total, a.cap_total);
+        if (hl.overflow || hr.overflow || base + total > a.cap_total) atomicOr(a.err, ERR_SLAB_OVERFLOW);
+    }
+    const int ny = a.g.ny;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int i = base + k;
+        if (i >= a.cap_total) break;
+        float4 r, c0 = make_float4(0.f, 0.f, 1.f, 0.f);
+        int4 c1;
+        int lcx, cy;
+        if (k < lm + lg) {
+            if (k < lm) { const MigRec& m = a.in_left.mig()[k]; r = m.rec; c0 = m.cold0; c1 = m.cold1; cy = m.cy; lcx = 1; }
+            else { const GhostRec& m = a.in_left.ghost()[k - lm]; r = m.rec; c1 = make_int4(0x7FFFFFFF, 0, 0, m.id); cy = m.cy; lcx = 0; }
+        } else {
+            const int kk = k - lm - lg;
+            if (kk < rm) { const MigRec& m = a.in_right.mig()[kk]; r = m.rec; c0 = m.cold0; c1 = m.cold1; cy = m.cy; lcx = a.g.lnx - 2; }
+            else { const GhostRec& m = a.in_right.ghost()[kk - rm]; r = m.rec; c1 = make_int4(0x7FFFFFFF, 0, 0, m.id); cy = m.cy; lcx = a.g.lnx - 1; }
+        }
+        const int c = lcx * ny + cy;
+        a.rec[i] = r; a.cold0[i] = c0; a.cold1[i] = c1;
+        a.next_cell[i] = c;
+        a.next_rank[i] = atomicAdd(&a.next_count[c], 1);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // K1 (ingest), K2 (scan), K3 (scatter)
 // ------------------------------------------------------------------------------------------------------
@@ -468,33 +590,49 @@ struct IngestArgs {
     const int* lag; const int* rate; const int* intake;
     float4* rec; float4* cold0; int4* cold1;
     int* next_cell; int* next_rank; int* next_count;
-    int n, nx, ny, id_base;
-    int* bad;  // set to 1 if a coordinate is outside [0,W] x [0,H] or not finite
+    int* n_unsorted;  // entry counter (atomic); a fish of a slab's edge columns can be held twice (owned + ghost)
+    int n_global, cap_total;
+    Grid g;
+    int* bad;  // set to 1 if a coordinate is outside [0,W] x [0,H] or not finite, 2 if the arrays overflow
     double w, h;
 };
 
+__device__ __forceinline__ void ingest_entry(const IngestArgs& a, int k, int lcx, int cy, const float4& r, const float4& c0, const int4& c1) {
+    if (k < 0) k = claim_slot(a.n_unsorted);
+    if (k >= a.cap_total) { atomicOr(a.bad, 2); return; }
+    const int c = lcx * a.g.ny + cy;
+    a.rec[k] = r; a.cold0[k] = c0; a.cold1[k] = c1;
+    a.next_cell[k] = c;
+    a.next_rank[k] = atomicAdd(&a.next_count[c], 1);
+}
+
 __global__ void ingest_kernel(const IngestArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= a.n_global) return;
     double x = a.coords[2 * (size_t)i], y = a.coords[2 * (size_t)i + 1];
-    if (!(x >= 0.0 && x <= a.w && y >= 0.0 && y <= a.h)) { *a.bad = 1; x = 0; y = 0; }
+    if (!(x >= 0.0 && x <= a.w && y >= 0.0 && y <= a.h)) { atomicOr(a.bad, 1); x = 0; y = 0; }
     if (x >= a.w) x -= a.w;  // x == W is kept by the reference's strict compare (fish_mod.cpp:468); here it wraps
     if (y >= a.h) y -= a.h;
     int cx = (int)floor(x / CELL_I), cy = (int)floor(y / CELL_I);
     float ox = (float)(x - (double)cx * CELL_I), oy = (float)(y - (double)cy * CELL_I);
     if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
     if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
-    if (cx >= a.nx) cx -= a.nx;
-    if (cy >= a.ny) cy -= a.ny;
+    if (cx >= a.g.nx_g) cx -= a.g.nx_g;
+    if (cy >= a.g.ny) cy -= a.g.ny;
     const float dirf = (float)a.dir[i];
     double sn, cs;
     sincospi((double)dirf / 180.0, &sn, &cs);
-    a.rec[i] = make_float4(ox, oy, (float)cs, (float)sn);
-    a.cold0[i] = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
-    a.cold1[i] = make_int4(a.lag[i], a.rate[i], a.intake[i], a.id_base + i);
-    const int c = cy * a.nx + cx;
-    a.next_cell[i] = c;
-    a.next_rank[i] = atomicAdd(&a.next_count[c], 1);
+    const float4 r = make_float4(ox, oy, (float)cs, (float)sn);
+    const float4 c0 = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
+    const int4 c1 = make_int4(a.lag[i], a.rate[i], a.intake[i], i);
+    if (a.g.wrap_x) { ingest_entry(a, i, cx, cy, r, c0, c1); return; }  // whole school: entry i, n_unsorted preset to n
+    // slab: local column of the fish's global column, as an owned entry and/or as a ghost of either halo column
+    int lo = cx - a.g.gx0 - 1; if (lo < 0) lo += a.g.nx_g;  // columns past the first owned one
+    lo += 1;
+    if (lo <= a.g.lnx - 2) ingest_entry(a, -1, lo, cy, r, c0, c1);
+    const int4 g1 = make_int4(0x7FFFFFFF, 0, 0, i);
+    if (cx == a.g.gx0) ingest_entry(a, -1, 0, cy, r, c0, g1);
+    if (cx == (a.g.gx0 + a.g.lnx - 1) % a.g.nx_g) ingest_entry(a, -1, a.g.lnx - 1, cy, r, c0, g1);
 }
 
 constexpr int SCAN_THREADS = 256;
@@ -568,12 +706,13 @@ struct ScatterArgs {
     const float4* rec_in; const float4* cold0_in; const int4* cold1_in;
     float4* rec_out; float4* cold0_out; int4* cold1_out; int* cell_out;
     const int* next_cell; const int* next_rank; const int* start;
-    int n;
+    const int* n_unsorted;
 };
 __global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= *a.n_unsorted) return;
     const int c = a.next_cell[i];
+    if (c < 0) return;  // last step's ghost
     const int dst = a.start[c] + a.next_rank[i];
     a.rec_out[dst] = a.rec_in[i];
     a.cold0_out[dst] = a.cold0_in[i];
@@ -582,69 +721,76 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// export / generic queries
+// export / generic queries.  Owned fish only.  pos = id (whole school: the caller's arrays are in id order) or
+// the fish's index inside the owned range plus an id list (slab: the host scatters the compact arrays by id).
 // ------------------------------------------------------------------------------------------------------
 struct ExportArgs {
-    const float4* rec; const float4* cold0; const int4* cold1; const int* cell;
-    double* coords; double* dir; double* speed; double* sf; int* lag; int* rate; int* intake;
-    int n, nx, id_base;
+    const float4* rec; const float4* cold0; const int4* cold1; const int* cell; const int* cell_start;
+    double* coords; double* dir; double* speed; double* sf; int* lag; int* rate; int* intake; int* ids;
+    Grid g;
+    int compact;
 };
 __global__ void export_kernel(const ExportArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const int own_b = a.cell_start[a.g.own_c0];
+    const int i = own_b + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cell_start[a.g.own_c1]) return;
     const float4 r = a.rec[i], c0 = a.cold0[i];
     const int4 c1 = a.cold1[i];
     const int c = a.cell[i];
-    const size_t id = (size_t)(c1.w - a.id_base);
+    const size_t pos = a.compact ? (size_t)(i - own_b) : (size_t)c1.w;
+    if (a.ids) a.ids[pos] = c1.w;
     if (a.coords) {
-        a.coords[2 * id] = (double)(c % a.nx) * CELL_I + (double)r.x;
-        a.coords[2 * id + 1] = (double)(c / a.nx) * CELL_I + (double)r.y;
+        const int gcx = (a.g.gx0 + c / a.g.ny) % a.g.nx_g;
+        a.coords[2 * pos] = (double)gcx * CELL_I + (double)r.x;
+        a.coords[2 * pos + 1] = (double)(c % a.g.ny) * CELL_I + (double)r.y;
     }
-    if (a.dir) a.dir[id] = (double)c0.x;
-    if (a.speed) a.speed[id] = (double)c0.y;
-    if (a.sf) a.sf[id] = (double)c0.z;
-    if (a.lag) a.lag[id] = c1.x;
-    if (a.rate) a.rate[id] = c1.y;
-    if (a.intake) a.intake[id] = c1.z;
+    if (a.dir) a.dir[pos] = (double)c0.x;
+    if (a.speed) a.speed[pos] = (double)c0.y;
+    if (a.sf) a.sf[pos] = (double)c0.z;
+    if (a.lag) a.lag[pos] = c1.x;
+    if (a.rate) a.rate[pos] = c1.y;
+    if (a.intake) a.intake[pos] = c1.z;
 }
 
-// per-pass outputs from sorted order to id order
+// per-pass outputs from sorted order to id (or compact) order
 struct ExportPassArgs {
-    const int4* cold1; const int4* cnt; const float* turn; const uint32_t* aux;
-    int* cnt4; double* turn_out; int* n_avoid; int* n_align; int* n_attract; double* speed_out;
-    int n, id_base; double speed_norm;
+    const int4* cold1; const int4* cnt; const float* turn; const uint32_t* aux; const int* cell_start;
+    int* cnt4; double* turn_out; int* n_avoid; int* n_align; int* n_attract; double* speed_out; int* ids;
+    Grid g;
+    int compact; double speed_norm;
 };
 __global__ void export_pass_kernel(const ExportPassArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const size_t id = (size_t)(a.cold1[i].w - a.id_base);
+    const int own_b = a.cell_start[a.g.own_c0];
+    const int i = own_b + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cell_start[a.g.own_c1]) return;
+    const int id = a.cold1[i].w;
+    const size_t pos = a.compact ? (size_t)(i - own_b) : (size_t)id;
     const int4 c = a.cnt[i];
-    if (a.cnt4) { a.cnt4[4 * id] = c.x; a.cnt4[4 * id + 1] = c.y; a.cnt4[4 * id + 2] = c.z; a.cnt4[4 * id + 3] = c.w; }
-    if (a.turn_out) a.turn_out[id] = (double)a.turn[i];
-    if (a.n_avoid) a.n_avoid[id] = c.x;
-    if (a.n_align) a.n_align[id] = c.y - c.x;
-    if (a.n_attract) a.n_attract[id] = c.z - c.y;
-    if (a.speed_out) a.speed_out[id] = 1.0 + 2.0 * (double)c.w / a.speed_norm;
+    if (a.ids) a.ids[pos] = id;
+    if (a.cnt4) { a.cnt4[4 * pos] = c.x; a.cnt4[4 * pos + 1] = c.y; a.cnt4[4 * pos + 2] = c.z; a.cnt4[4 * pos + 3] = c.w; }
+    if (a.turn_out) a.turn_out[pos] = (double)a.turn[i];
+    if (a.n_avoid) a.n_avoid[pos] = c.x;
+    if (a.n_align) a.n_align[pos] = c.y - c.x;
+    if (a.n_attract) a.n_attract[pos] = c.z - c.y;
+    if (a.speed_out) a.speed_out[pos] = 1.0 + 2.0 * (double)c.w / a.speed_norm;
 }
 
 // in_zone(inds,id,fov,r) for arbitrary fov / r <= 200: literal fp64 predicate over the 3x3 stencil
 struct ZoneArgs {
     const float4* rec; const float4* cold0; const int4* cold1; const int* cell; const int* cell_start;
-    int* out; int n, nx, ny, id_base, fov_half; double r;
+    int* out; int* ids; Grid g; int compact, fov_half; double r;
 };
 __global__ void in_zone_generic_kernel(const ZoneArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const int own_b = a.cell_start[a.g.own_c0];
+    const int i = own_b + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cell_start[a.g.own_c1]) return;
     const float4 me = a.rec[i];
-    const int c = a.cell[i], cx = c % a.nx, cy = c / a.nx;
+    const int c = a.cell[i];
     const double ang = __ddiv_rn(__dmul_rn((double)a.cold0[i].x, M_PI), 180.0);
     const double cs = cos(ang), sn = sin(ang);
     int count = 0;
     for (int k = 0; k < 9; ++k) {
-        int xx = cx + (k % 3) - 1, yy = cy + (k / 3) - 1;
-        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
-        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
-        const int cc = yy * a.nx + xx;
+        const int cc = stencil_cell(a.g, c, k);
         const double sx = (double)((k % 3) - 1) * 200.0, sy = (double)((k / 3) - 1) * 200.0;
         for (int j = a.cell_start[cc]; j < a.cell_start[cc + 1]; ++j) {
             if (j == i) continue;
@@ -657,7 +803,10 @@ __global__ void in_zone_generic_kernel(const ZoneArgs a) {
             if (angle < (double)a.fov_half && dist < a.r) count++;
         }
     }
-    a.out[a.cold1[i].w - a.id_base] = count;
+    const int id = a.cold1[i].w;
+    const size_t pos = a.compact ? (size_t)(i - own_b) : (size_t)id;
+    a.out[pos] = count;
+    if (a.ids) a.ids[pos] = id;
 }
 
 __global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long long* out) {
@@ -667,25 +816,27 @@ __global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long lon
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
-// feed(inds,id,...) for an explicit id list, sequentially (fish_mod.cpp:560-574); API completeness, not hot
+// feed(inds,id,...) for an explicit id list, sequentially (fish_mod.cpp:560-574); API completeness, not hot.
+// Ids this context does not own are skipped.
 struct FeedArgs {
     float4* cold0; int4* cold1; const float4* rec; const int* cell; const int* ids; int k;
-    uint8_t* quality; int n, nx, qcols, id_base; int* pos_of_id;
+    uint8_t* quality; int n_global, qcols; Grid g; int* pos_of_id;
 };
-__global__ void index_by_id_kernel(const int4* cold1, int n, int id_base, int* pos_of_id) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) pos_of_id[cold1[i].w - id_base] = i;
+__global__ void index_by_id_kernel(const int4* cold1, const int* cell_start, Grid g, int* pos_of_id) {
+    const int i = cell_start[g.own_c0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cell_start[g.own_c1]) pos_of_id[cold1[i].w] = i;
 }
 __global__ void feed_list_kernel(const FeedArgs a) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     for (int t = 0; t < a.k; ++t) {
         const int id = a.ids[t];
-        if (id < 0 || id >= a.n) continue;
+        if (id < 0 || id >= a.n_global) continue;
         const int i = a.pos_of_id[id];
+        if (i < 0) continue;
         const float4 r = a.rec[i];
         const int c = a.cell[i];
-        const int gx = (c % a.nx) * FOOD_PER_CELL + min((int)r.x / FOOD_I, FOOD_PER_CELL - 1);
-        const int gy = (c / a.nx) * FOOD_PER_CELL + min((int)r.y / FOOD_I, FOOD_PER_CELL - 1);
+        const int gx = (c / a.g.ny - a.g.own_c0 / a.g.ny) * FOOD_PER_CELL + min((int)r.x / FOOD_I, FOOD_PER_CELL - 1);
+        const int gy = (c % a.g.ny) * FOOD_PER_CELL + min((int)r.y / FOOD_I, FOOD_PER_CELL - 1);
         const int qi = gy * a.qcols + gx;
         const int q = a.quality[qi];
         float4 c0 = a.cold0[i];

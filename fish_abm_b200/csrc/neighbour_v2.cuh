@@ -56,17 +56,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
     while (true) {
     int c = 0;
     if (lane == 0) c = atomicAdd(a.work_counter, 1);
-    c = __shfl_sync(FULL, c, 0);
-    if (c >= a.ncell) break;
+    c = a.g.own_c0 + __shfl_sync(FULL, c, 0);
+    if (c >= a.g.own_c1) break;
     const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
     if (s0 == e0) continue;
-    const int cx = c % a.nx, cy = c / a.nx;
     int nb_s = 0, nb_e = 0;
     if (lane < 9) {
-        int xx = cx + (lane % 3) - 1, yy = cy + (lane / 3) - 1;
-        xx = xx < 0 ? xx + a.nx : (xx >= a.nx ? xx - a.nx : xx);
-        yy = yy < 0 ? yy + a.ny : (yy >= a.ny ? yy - a.ny : yy);
-        const int cc = yy * a.nx + xx;
+        const int cc = stencil_cell(a.g, c, lane);
         nb_s = a.cell_start[cc];
         nb_e = a.cell_start[cc + 1];
     }

@@ -24,11 +24,18 @@ class School:
     """One school resident on one GPU.  Method names follow the reference's functions."""
 
     def __init__(self, n: int = 60, w: int = 2000, h: int = 2000, seed: int = 0, device: int = 0,
-                 rolling: bool = True, speed_norm: float = 0.0, mode: int = _lib.MODE_CELL_FP32):
+                 rolling: bool = True, speed_norm: float = 0.0, mode: int = _lib.MODE_CELL_FP32,
+                 rank: int = 0, nranks: int = 1, force_slab: bool = False, capacity: int = 0, halo_capacity: int = 0,
+                 migrant_capacity: int = 0):
+        """rank / nranks > 1: this context is one x-slab of the school (see include/fishabm.h and slab.py); n, w, h and
+        every array passed in or out still describe the WHOLE school."""
         self.L = _lib.load()
         p = _lib.Params()
         self.L.fishabm_params_default(C.byref(p))
         p.n, p.w, p.h, p.seed, p.device, p.rolling, p.speed_norm, p.mode = n, w, h, seed, device, int(rolling), speed_norm, mode
+        p.rank, p.nranks, p.force_slab = rank, nranks, int(force_slab)
+        p.capacity, p.halo_capacity, p.migrant_capacity = capacity, halo_capacity, migrant_capacity
+        self.is_slab = nranks > 1 or force_slab
         self.params = p
         self.ctx = C.c_void_p()
         rc = self.L.fishabm_create(C.byref(p), C.byref(self.ctx))
@@ -68,13 +75,24 @@ class School:
         self._ck(self.L.fishabm_set_state(self.ctx, _p(coords), _p(dir), _p(speed), _p(speed_factor), _p(lag),
                                           _p(sample_rate), _p(food_intake)))
 
+    NOT_OWNED = np.iinfo(np.int32).min
+
     def get_state(self) -> dict:
+        """Whole school: every fish.  Slab: only the entries of the fish this slab owns are written; the others keep
+        NaN / NOT_OWNED (see owned_mask)."""
         n = self.n
         out = dict(coords=np.empty((n, 2)), dir=np.empty(n), speed=np.empty(n), speed_factor=np.empty(n),
                    lag=np.empty(n, np.int32), sample_rate=np.empty(n, np.int32), food_intake=np.empty(n, np.int32))
+        if self.is_slab:
+            for v in out.values():
+                v.fill(np.nan if v.dtype == np.float64 else self.NOT_OWNED)
         self._ck(self.L.fishabm_get_state(self.ctx, *(_p(out[k]) for k in
                                                       ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake"))))
         return out
+
+    @staticmethod
+    def owned_mask(state: dict) -> np.ndarray:
+        return state["lag"] != School.NOT_OWNED
 
     def initialize(self, speed: float = 5.0):
         """initialize(fish, num, 2, speed, struc), fish_mod.cpp:116,183-206"""
@@ -86,7 +104,8 @@ class School:
         self._ck(self.L.fishabm_set_quality(self.ctx, _p(q), q.shape[0], q.shape[1], q.shape[1]))
 
     def get_quality(self) -> np.ndarray:
-        q = np.empty((self.rows, self.cols), np.int32)
+        """Whole school: the grid.  Slab: the owned columns, -1 elsewhere."""
+        q = np.full((self.rows, self.cols), -1, np.int32)
         self._ck(self.L.fishabm_get_quality(self.ctx, 0, _p(q), self.rows, self.cols, self.cols))
         return q
 
@@ -108,23 +127,23 @@ class School:
 
     # ---- frozen-state queries --------------------------------------------------------------------------------
     def in_zone(self, fov: int, r: float) -> np.ndarray:
-        out = np.empty(self.n, np.int32)
+        out = np.full(self.n, -1, np.int32)
         self._ck(self.L.fishabm_in_zone(self.ctx, int(fov), float(r), _p(out)))
         return out
 
     def zone_counts(self) -> np.ndarray:
-        out = np.empty((self.n, 4), np.int32)
+        out = np.full((self.n, 4), -1, np.int32)
         self._ck(self.L.fishabm_zone_counts(self.ctx, _p(out)))
         return out
 
     def social(self):
-        turn = np.empty(self.n)
-        na, nl, nt = (np.empty(self.n, np.int32) for _ in range(3))
+        turn = np.full(self.n, np.nan)
+        na, nl, nt = (np.full(self.n, -1, np.int32) for _ in range(3))
         self._ck(self.L.fishabm_social(self.ctx, _p(turn), _p(na), _p(nl), _p(nt)))
         return turn, na, nl, nt
 
     def get_speed(self) -> np.ndarray:
-        out = np.empty(self.n)
+        out = np.full(self.n, np.nan)
         self._ck(self.L.fishabm_get_speed(self.ctx, _p(out)))
         return out
 
@@ -191,6 +210,39 @@ class School:
         v = C.c_uint64(0)
         self.L.fishabm_launch_count(self.ctx, C.byref(v))
         return int(v.value)
+
+    # ---- slab decomposition ------------------------------------------------------------------------------------------
+    def slab_info(self) -> dict:
+        s = _lib.SlabInfo()
+        self._ck(self.L.fishabm_slab_get_info(self.ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def slab_connect(self, unique_id: bytes):
+        buf = (C.c_char * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._ck(self.L.fishabm_slab_connect(self.ctx, C.cast(buf, C.c_void_p), _lib.UNIQUE_ID_BYTES))
+
+    def slab_begin_step(self):
+        self._ck(self.L.fishabm_slab_begin_step(self.ctx))
+
+    def slab_end_step(self):
+        self._ck(self.L.fishabm_slab_end_step(self.ctx))
+
+    def slab_buffers(self):
+        """(out_left, out_right, in_left, in_right) device pointers and the message size in bytes"""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        nbytes = C.c_int64(0)
+        self._ck(self.L.fishabm_slab_buffers(self.ctx, *(C.byref(p) for p in ptrs), C.byref(nbytes)))
+        return tuple(p.value for p in ptrs), int(nbytes.value)
+
+
+def slab_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)"""
+    L = _lib.load()
+    buf = (C.c_char * _lib.UNIQUE_ID_BYTES)()
+    rc = L.fishabm_slab_unique_id(C.cast(buf, C.c_void_p), _lib.UNIQUE_ID_BYTES)
+    if rc != 0:
+        raise FishAbmError(rc, L.fishabm_last_error(None).decode())
+    return bytes(buf)
 
 
 def averageturn(v, comb_weight: bool = False) -> float:

@@ -1,0 +1,267 @@
+"""One school split into x-slabs across GPUs (BASELINE.json north_star).  No reference counterpart:
+fish_mod.cpp is single-threaded.  The decomposition itself lives in libfishabm.so (include/fishabm.h, "slab
+decomposition"); this module is the host plumbing around it:
+
+  partition / ring   the column split and ring neighbours the library uses (restated for host-side checks)
+  broadcast_unique_id, connect   NCCL bootstrap over an existing torch.distributed group (any backend)
+  DistributedSchool  one rank's slab in a one-process-per-GPU job; the exchange runs inside the library (NCCL)
+  LocalSlabs         several slabs in ONE process (one or more GPUs), the exchange driven from here through the
+                     caller-driven hooks: used to test the decomposition on a single GPU
+  merge_owned        assemble per-slab outputs into whole-school arrays
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from .school import School, slab_unique_id
+
+
+def partition(nx: int, nranks: int):
+    """owned cell columns [col0, col1) of every rank: col_r = floor(r*nx/nranks)"""
+    return [(r * nx // nranks, (r + 1) * nx // nranks) for r in range(nranks)]
+
+
+def ring(rank: int, nranks: int):
+    """(left, right) neighbours in the periodic world"""
+    return (rank - 1) % nranks, (rank + 1) % nranks
+
+
+def merge_owned(parts, not_owned):
+    """parts: per-slab arrays of identical shape in which entries a slab does not own hold `not_owned` (NaN allowed).
+    Every entry must be owned by exactly one slab."""
+    out = np.array(parts[0], copy=True)
+    seen = np.zeros(out.shape[0], np.int32)
+    for p in parts:
+        own = ~np.isnan(p) if (isinstance(not_owned, float) and np.isnan(not_owned)) else (p != not_owned)
+        own = own.reshape(own.shape[0], -1).any(axis=1) if own.ndim > 1 else own
+        out[own] = p[own]
+        seen += own
+    if not np.all(seen == 1):
+        raise ValueError(f"ownership is not a partition: {np.count_nonzero(seen == 0)} unowned, {np.count_nonzero(seen > 1)} multiply owned")
+    return out
+
+
+def merge_states(states):
+    """whole-school state dict from the per-slab get_state() dicts"""
+    masks = [School.owned_mask(s) for s in states]
+    seen = np.sum(masks, axis=0)
+    if not np.all(seen == 1):
+        raise ValueError(f"ownership is not a partition: {np.count_nonzero(seen == 0)} unowned, {np.count_nonzero(seen > 1)} multiply owned")
+    out = {k: np.array(v, copy=True) for k, v in states[0].items()}
+    for s, m in zip(states[1:], masks[1:]):
+        for k in out:
+            out[k][m] = s[k][m]
+    return out
+
+
+def merge_quality(grids):
+    out = np.array(grids[0], copy=True)
+    for g in grids[1:]:
+        m = g >= 0
+        if np.any(m & (out >= 0)):
+            raise ValueError("food columns owned twice")
+        out[m] = g[m]
+    if np.any(out < 0):
+        raise ValueError("food columns unowned")
+    return out
+
+
+# ---- NCCL bootstrap over torch.distributed ------------------------------------------------------------------------------
+def broadcast_unique_id(dist, rank: int, device=None) -> bytes:
+    """rank 0 creates the NCCL unique id (through the library) and every rank of the torch.distributed group gets it"""
+    import torch
+    t = torch.zeros(_lib.UNIQUE_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(slab_unique_id()), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+class DistributedSchool(School):
+    """This rank's slab.  `dist` is an initialised torch.distributed module/group used only for the bootstrap."""
+
+    def __init__(self, dist, rank: int, nranks: int, device: int, **kw):
+        super().__init__(rank=rank, nranks=nranks, device=device, **kw)
+        if nranks > 1:
+            import torch
+            dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else None
+            self.slab_connect(broadcast_unique_id(dist, rank, dev))
+
+
+# ---- several slabs in one process -----------------------------------------------------------------------------------------
+class LocalSlabs:
+    """nslabs contexts in this process; step() drives the exchange through the caller-driven hooks
+    (fishabm_slab_begin_step / fishabm_slab_buffers / fishabm_slab_end_step)."""
+
+    def __init__(self, nslabs: int, devices=None, **kw):
+        self.k = nslabs
+        devices = devices or [0] * nslabs
+        self.S = [School(rank=r, nranks=nslabs, device=devices[r], force_slab=True, **kw) for r in range(nslabs)]
+        self.n, self.w, self.h = self.S[0].n, self.S[0].w, self.S[0].h
+
+    def close(self):
+        for s in self.S:
+            s.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_state(self, **d):
+        for s in self.S:
+            s.set_state(**d)
+
+    def set_quality(self, q):
+        for s in self.S:
+            s.set_quality(q)
+
+    def set_step_index(self, v: int):
+        for s in self.S:
+            s.step_index = v
+
+    def step(self, nsteps: int = 1):
+        L = self.S[0].L
+        for _ in range(nsteps):
+            for s in self.S:
+                s.slab_begin_step()
+            bufs = [s.slab_buffers() for s in self.S]
+            for r in range(self.k):
+                (out_l, out_r, _, _), nbytes = bufs[r]
+                left, right = ring(r, self.k)
+                # what leaves through my left edge arrives at my left neighbour's right side, and vice versa
+                assert L.fishabm_slab_copy(bufs[left][0][3], out_l, nbytes) == 0
+                assert L.fishabm_slab_copy(bufs[right][0][2], out_r, nbytes) == 0
+            for s in self.S:
+                s.slab_end_step()
+
+    def get_state(self):
+        return merge_states([s.get_state() for s in self.S])
+
+    def get_quality(self):
+        return merge_quality([s.get_quality() for s in self.S])
+
+    def sum_array(self) -> int:
+        return sum(s.sum_array() for s in self.S)
+
+    def zone_counts(self):
+        return merge_owned([s.zone_counts() for s in self.S], -1)
+
+    def social_turn(self):
+        return merge_owned([s.social()[0] for s in self.S], float("nan"))
+
+    def in_zone(self, fov, r):
+        return merge_owned([s.in_zone(fov, r) for s in self.S], -1)
+
+
+# ---- the multi-GPU benchmark leg (bench.py --gpus N, N > 1) ----------------------------------------------------------------
+def run_slab_bench(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from . import synth
+    from bench import N_C4, ClockSampler, measured_peaks, flops_alg, FP32_LANES_PER_SM, ROOT
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.fish or N_C4
+    w = synth.world_size_for(n)
+    q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+    d = synth.uniform_state(n, w, w, seed=0x5EED)   # every rank composes the same whole-school state ...
+    q = synth.tile_quality(q100, w, w)
+    S = DistributedSchool(dist, rank, world, local_rank, n=n, w=w, h=w, seed=0x5EED)
+    S.set_state(**d)                                 # ... and keeps its own columns
+    S.set_quality(q)
+    info = S.slab_info()
+    del q
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        S.step(1)
+    S.flush()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = S.launch_count()
+    # K steps in one library call per rank: neighbour pass, update+pack, NCCL exchange, ingest, sort, all on the
+    # library's stream with no host synchronisation in between; the trailing sample() is part of the K steps
+    t0 = time.perf_counter()
+    S.step(args.steps)
+    ms = S.last_step_ms()
+    nb_ms, nb_l = S.last_neighbour_ms()
+    S.flush()
+    ms += S.last_step_ms()
+    a, b = S.last_neighbour_ms(); nb_ms += a; nb_l += b
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = S.launch_count() - launches0
+    clk = clocks.stop()
+    t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, wall_max = float(t[0]), float(t[1])
+
+    # pair counters of one pass for the roofline line (rank-local work, summed over ranks)
+    S.enable_stats(True)
+    S.step(1)
+    st = S.last_pass_stats()
+    S.flush()
+    S.enable_stats(False)
+    c = torch.tensor([st["candidates"], st["interacting"], st["focal"], launches, nb_ms, nb_l, info["owned"]], dtype=torch.float64, device="cuda")
+    cs = c.clone(); dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    cm = c.clone(); dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+
+    # end to end: host arrays in, host arrays out, every step (rank-local H2D of the whole-school arrays is what the
+    # C ABI's set_state takes; D2H returns the owned fish)
+    e2e_steps = 2
+    g = None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        S.set_state(**d)
+        S.step(1)
+        g = S.get_state()
+        S.sum_array()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d = sum(v.nbytes for v in d.values())
+    d2h = int(info["owned"]) * 52 + 8
+    S.close()
+    if rank == 0:
+        peaks, how = measured_peaks()
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        per_launch_ms = float(cm[4]) / max(float(cm[5]), 1.0)           # slowest rank's average neighbour launch
+        flops = flops_alg(float(cs[0]), float(cs[1])) / world            # per rank, per launch
+        achieved = flops / (per_launch_ms * 1e-3) / 1e12
+        line = {"metric": "agent_steps_per_sec", "value": n * args.steps / (ms_max * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C4: N={n} school, W=H={w} periodic, {world} x-slabs with 200-unit halos + migration over NCCL, "
+                                       f"cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0" if n == N_C4 else f"N={n}, W=H={w}, {world} slabs",
+                           "n_fish": n, "world": w, "parallelism": f"slab{world}", "l2": "per-rank state larger than L2" if n // world * 76 > (126 << 20) else "state fits L2, not flushed",
+                           "timing": "CUDA events on each rank's library stream around fishabm_step(K) + the trailing sample pass, max over ranks",
+                           "message_bytes_per_neighbour_per_step": info["message_bytes"], "wall_ms_per_step_max": wall_max / args.steps},
+                "clocks": clk, "gpu_launches": int(cs[3]),
+                "e2e": {"value": n * e2e_steps / float(te[0]), "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(float(cs[6])) * 52 + 8 * world,
+                        "steps": e2e_steps, "api": "per rank: fishabm_set_state(whole-school host arrays) + fishabm_step(1) + fishabm_get_state(owned fish) + fishabm_sum_quality"},
+                "roofline": {"bound": "fp32", "kernel": "neighbour_kernel_v2", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": achieved / fp32_peak, "traffic": None, "per": "rank (slowest rank's launch time, mean rank's pairs)",
+                             "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock)", "flops_per_launch": flops,
+                             "launch_ms": per_launch_ms, "share_of_step": float(cm[4]) / ms_max},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -70,7 +70,12 @@ typedef struct fishabm_params {
     /* slab decomposition of one school across GPUs (one context per rank); 1 rank = whole world */
     int32_t rank, nranks;
     int32_t n_global;      /* fish in the whole school when nranks > 1 (0 = n) */
-    int32_t capacity;      /* per-rank fish capacity when nranks > 1 (0 = automatic) */
+    int32_t capacity;      /* per-rank entry capacity (owned fish + ghosts + one step's arrivals) when slabs are used
+                              (0 = automatic: 1.3 x the uniform-density expectation) */
+    int32_t halo_capacity;    /* ghosts per slab message (0 = automatic: 2 x fish per cell column + 4096) */
+    int32_t migrant_capacity; /* migrants per slab message (0 = automatic) */
+    int32_t force_slab;    /* 1 = use halo columns and the message path even with nranks == 1 (the slab is then its own
+                              neighbour); for testing the decomposition on one GPU */
 } fishabm_params;
 
 /* pair counters of the most recent neighbour pass (for the roofline accounting) */
@@ -154,8 +159,37 @@ int fishabm_launch_count(const fishabm_ctx* ctx, uint64_t* out);
 /* enable pair counters (small cost) */
 int fishabm_enable_stats(fishabm_ctx* ctx, int32_t on);
 
-/* ---- slab exchange hooks (nranks > 1; the caller moves the packed buffers between ranks, e.g. NCCL) --- */
-/* see INTEGRATION.md; declared in fishabm_slab.h */
+/* ---- slab decomposition: one school split along x over nranks GPUs, one context per rank ---------------------
+ * (no reference counterpart: fish_mod.cpp is single-threaded; BASELINE.json north_star asks for it.)
+ * Rank r owns the cell columns [r*nx/nranks, (r+1)*nx/nranks) of the nx = w/200 columns (at least 2 each, so
+ * nranks <= nx/2), plus one halo column per side.  In slab mode fishabm_set_state / fishabm_set_quality take the GLOBAL arrays (n_global fish, the whole grid)
+ * on every rank and keep the rank's part; fishabm_get_state / get_quality / the frozen-state queries write only the
+ * entries of the fish (columns) the rank owns and leave the rest of the caller's arrays untouched;
+ * fishabm_sum_quality returns the rank's partial sum.  Integer state is bit-identical for any nranks.
+ *
+ * After every move() each slab sends ONE fixed-size message to each neighbour (migrants + its boundary column as
+ * the neighbour's next halo).  With fishabm_slab_connect the library moves them itself with NCCL send/recv on its
+ * own stream (no host synchronisation per step).  Without it the caller moves them: begin_step, copy each
+ * out_left -> left neighbour's in_right and out_right -> right neighbour's in_left, end_step. */
+#define FISHABM_UNIQUE_ID_BYTES 128
+typedef struct fishabm_slab_info {
+    int32_t rank, nranks, left, right;   /* ring neighbours (periodic world) */
+    int32_t col0, col1;                  /* owned global cell columns [col0, col1) */
+    int32_t owned, held;                 /* fish owned now; entries held now (owned + ghosts) */
+    int32_t capacity, halo_capacity, migrant_capacity;
+    int64_t message_bytes;
+} fishabm_slab_info;
+int fishabm_slab_get_info(fishabm_ctx* ctx, fishabm_slab_info* out);
+/* ncclGetUniqueId (rank 0; distribute the bytes to the other ranks by any means) */
+int fishabm_slab_unique_id(void* id_out, int32_t bytes);
+/* ncclCommInitRank with the context's rank / nranks on its device; collective over all ranks */
+int fishabm_slab_connect(fishabm_ctx* ctx, const void* id, int32_t bytes);
+/* caller-driven exchange */
+int fishabm_slab_begin_step(fishabm_ctx* ctx);
+int fishabm_slab_buffers(fishabm_ctx* ctx, void** out_left, void** out_right, void** in_left, void** in_right, int64_t* bytes);
+int fishabm_slab_end_step(fishabm_ctx* ctx);
+/* device-to-device copy helper for the caller-driven exchange (cudaMemcpy, synchronous) */
+int fishabm_slab_copy(void* dst_device, const void* src_device, int64_t bytes);
 
 /* ---- host-side scalar helpers with the reference's semantics (not on the hot path) ---------------------- */
 double fishabm_averageturn(const double* v, int32_t n, int32_t comb_weight); /* fish_mod.cpp:379-408 */

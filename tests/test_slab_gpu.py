@@ -1,0 +1,137 @@
+"""Slab decomposition (one school split along x): any number of slabs must reproduce the whole-school
+run bit for bit -- positions, headings, integer state and the food grid -- because pair sums are integers, feeding
+ranks are by global id inside one food cell, and draws are keyed by global id."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from fish_abm_b200 import School, synth
+from fish_abm_b200.slab import LocalSlabs, partition
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake")
+
+
+def whole_school(n, w, d, q, seed, steps):
+    with School(n=n, w=w, h=w, seed=seed) as S:
+        S.set_state(**d)
+        S.set_quality(q)
+        zc0 = S.zone_counts()
+        S.step(steps)
+        return zc0, S.get_state(), S.get_quality(), S.zone_counts(), S.social()[0]
+
+
+def assert_same(a, b):
+    for k in FIELDS:
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("n,w,steps,speed", [(20_000, 6400, 12, 5.0), (3_000, 1000 * 2, 25, 20.0), (400, 600, 30, 30.0)])
+def test_single_slab_with_halo_columns_equals_whole_school(q100, n, w, steps, speed):
+    """force_slab: the slab is its own neighbour on both sides; every fish crossing x=0 migrates through a message"""
+    d = synth.uniform_state(n, w, w, seed=41, speed=speed)
+    q = synth.tile_quality(q100, w, w)
+    zc0, g, qa, zc1, turn = whole_school(n, w, d, q, 77, steps)
+    with School(n=n, w=w, h=w, seed=77, force_slab=True) as S:
+        S.set_state(**d)
+        S.set_quality(q)
+        assert np.array_equal(S.zone_counts(), zc0)
+        S.step(steps)
+        assert_same(S.get_state(), g)
+        assert np.array_equal(S.get_quality(), qa)
+        assert np.array_equal(S.zone_counts(), zc1)
+        assert np.array_equal(S.social()[0], turn)
+        info = S.slab_info()
+        assert info["owned"] == n and info["held"] > n
+
+
+@pytest.mark.parametrize("nslabs", [2, 3, 4, 7])
+def test_local_slabs_equal_whole_school(q100, nslabs):
+    n, w, steps = 30_000, 7 * 200 * 2, 15  # 14 cell columns: uneven splits for 3 and 4 slabs, 2 columns each for 7
+    d = synth.uniform_state(n, w, w, seed=43, speed=12.0)
+    q = synth.tile_quality(q100, w, w)
+    zc0, g, qa, zc1, turn = whole_school(n, w, d, q, 78, steps)
+    with LocalSlabs(nslabs, n=n, w=w, h=w, seed=78) as P:
+        P.set_state(**d)
+        P.set_quality(q)
+        cols = [(s.slab_info()["col0"], s.slab_info()["col1"]) for s in P.S]
+        assert cols == partition(w // 200, nslabs)
+        assert sum(s.slab_info()["owned"] for s in P.S) == n
+        assert np.array_equal(P.zone_counts(), zc0)
+        P.step(steps)
+        assert sum(s.slab_info()["owned"] for s in P.S) == n  # migration conserves fish
+        assert_same(P.get_state(), g)
+        assert np.array_equal(P.get_quality(), qa)
+        assert np.array_equal(P.zone_counts(), zc1)
+        assert np.array_equal(P.social_turn(), turn)
+        assert P.sum_array() == int(qa.sum())
+
+
+def test_one_column_slabs_are_rejected(q100):
+    """a slab needs two owned columns (a migrant into a one-column slab would also be a ghost for the slab beyond)"""
+    from fish_abm_b200 import FishAbmError
+    with pytest.raises(FishAbmError) as e:
+        School(n=2000, w=1000, h=1000, rank=0, nranks=3)
+    assert e.value.code == -1 and "2 of the 5 cell columns" in str(e.value)
+    School(n=2000, w=1000, h=1000, rank=1, nranks=2).close()
+
+
+def test_slab_capacity_overflow_is_reported(q100):
+    from fish_abm_b200 import FishAbmError
+    n, w = 20_000, 2000
+    d = synth.uniform_state(n, w, w, seed=45)
+    with School(n=n, w=w, h=w, seed=1, force_slab=True, halo_capacity=16) as S:
+        S.set_state(**d)
+        S.set_quality(synth.tile_quality(q100, w, w))
+        with pytest.raises(FishAbmError) as e:
+            S.step(1)
+        assert e.value.code == -4 and "capacity" in str(e.value)
+    with pytest.raises(FishAbmError):
+        with School(n=n, w=w, h=w, seed=1, force_slab=True, capacity=1000) as S:
+            S.set_state(**d)
+
+
+def test_slab_rejects_fast_fish(q100):
+    from fish_abm_b200 import FishAbmError
+    d = synth.uniform_state(100, 2000, 2000, seed=46, speed=70.0)
+    with School(n=100, w=2000, h=2000, force_slab=True) as S:
+        with pytest.raises(FishAbmError):
+            S.set_state(**d)
+
+
+def test_unconnected_multi_rank_step_fails_loudly(q100):
+    from fish_abm_b200 import FishAbmError
+    d = synth.uniform_state(1000, 2000, 2000, seed=47)
+    with School(n=1000, w=2000, h=2000, rank=0, nranks=2) as S:
+        S.set_state(**d)
+        S.set_quality(q100)
+        with pytest.raises(FishAbmError) as e:
+            S.step(1)
+        assert e.value.code == -3
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_nccl_slabs_equal_whole_school(q100, tmp_path, nranks):
+    """one process per GPU, exchange inside the library over NCCL; needs that many GPUs on the box"""
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    out = tmp_path / "res.npz"
+    port = 29650 + nranks
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = np.load(out)
+    n, w, steps, seed = int(res["n"]), int(res["w"]), int(res["steps"]), int(res["seed"])
+    d = synth.uniform_state(n, w, w, seed=51, speed=10.0)
+    q = synth.tile_quality(q100, w, w)
+    _, g, qa, zc1, _ = whole_school(n, w, d, q, seed, steps)
+    for k in FIELDS:
+        assert np.array_equal(res[k], g[k]), k
+    assert np.array_equal(res["quality"], qa)
+    assert np.array_equal(res["zone"], zc1)
