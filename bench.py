@@ -242,13 +242,15 @@ def ours(args, rank: int, world: int, local_rank: int):
     order = ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake")
     sumq = np.zeros(1, np.int64)
 
+    bufs = [host, out]
+
     def e2e_step():
-        S._ck(S.L.fishabm_set_state(S.ctx, *(_p(host[k]) for k in order)))
+        src, dst = bufs  # the state a step returns is the next step's input: the two pinned sets swap roles
+        S._ck(S.L.fishabm_set_state(S.ctx, *(_p(src[k]) for k in order)))
         S._ck(S.L.fishabm_step(S.ctx, 1))
-        S._ck(S.L.fishabm_get_state(S.ctx, *(_p(out[k]) for k in order)))
+        S._ck(S.L.fishabm_get_state(S.ctx, *(_p(dst[k]) for k in order)))
         S._ck(S.L.fishabm_sum_quality(S.ctx, _p(sumq)))
-        for k in order:
-            host[k][...] = out[k]
+        bufs.reverse()
 
     e2e_step()
     torch.cuda.synchronize()
