@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfishabm.so")
 
 OK, E_ARG, E_CUDA, E_STATE, E_NOMEM, E_COMM = 0, -1, -2, -3, -4, -5
-MODE_CELL_FP32, MODE_BRUTE_FP64 = 0, 1
+MODE_CELL_FP32, MODE_BRUTE_FP64, MODE_ENSEMBLE = 0, 1, 2
 STREAM_CHOICE, STREAM_ERROR, STREAM_RANDOMWALK, STREAM_QUALITY, STREAM_SEED, STREAM_SAMPLE, STREAM_INIT = range(7)
 
 
@@ -18,7 +18,7 @@ class Params(C.Structure):
                 ("mode", C.c_int32), ("device", C.c_int32), ("replicates", C.c_int32), ("rolling", C.c_int32),
                 ("seed", C.c_uint64), ("speed_norm", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("n_global", C.c_int32), ("capacity", C.c_int32), ("halo_capacity", C.c_int32),
-                ("migrant_capacity", C.c_int32), ("force_slab", C.c_int32)]
+                ("migrant_capacity", C.c_int32), ("replicate0", C.c_uint32), ("force_slab", C.c_int32)]
 
 
 class SlabInfo(C.Structure):

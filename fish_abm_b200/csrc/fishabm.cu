@@ -16,6 +16,7 @@
 
 #include "kernels.cuh"
 #include "neighbour_v2.cuh"
+#include "ensemble.cuh"
 
 using namespace fishk;
 
@@ -44,6 +45,10 @@ struct fishabm_ctx {
     Grid g;               // local grid (kernels.cuh)
     int ncell = 0, qrows = 0, qcols = 0;   // local cells; food grid held here: qrows x qcols (owned columns)
     int qcols_g = 0, qcol0 = 0;            // global food columns; first owned food column
+    bool ens = false;     // replicate ensemble (ensemble.cuh): R schools of n fish, arrays hold R*n entries
+    int R = 1;
+    size_t ens_smem = 0;
+    long long* d_sums = nullptr;   // [R]
     bool slab = false;    // halo columns + message path
     int own = 0, col0 = 0, left = 0, right = 0;
     int cap_m = 0, cap_g = 0;
@@ -159,7 +164,7 @@ int rebuild(fishabm_ctx* ctx) {
     scan_finish_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start);
     const Buffers& in = ctx->buf[ctx->cur];
     const Buffers& out = ctx->buf[ctx->cur ^ 1];
-    ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted};
+    ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap};
     scatter_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(s);
     ctx->launches += 4;
     ctx->cur ^= 1;
@@ -177,7 +182,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.cnt = ctx->cnt; a.turn = ctx->turn; a.aux = ctx->aux; a.stats = ctx->stats_on ? ctx->stats : nullptr;
     a.g = ctx->g;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
-    a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = 0;
+    a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = ctx->p.replicate0;
     a.work_counter = ctx->work_counter;
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -219,7 +224,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.err = ctx->err;
     u.g = ctx->g; u.qcols = ctx->qcols;
     u.do_sample = do_sample; u.do_move = do_move; u.rolling = ctx->p.rolling;
-    u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = 0; u.speed_norm = ctx->speed_norm;
+    u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = ctx->p.replicate0; u.speed_norm = ctx->speed_norm;
     u.slab = ctx->slab ? 1 : 0;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) {
@@ -349,6 +354,51 @@ int fetch_ids(fishabm_ctx* ctx, int count) {
     return 0;
 }
 
+// ---- replicate ensembles --------------------------------------------------------------------------------------------
+EnsembleArgs ens_args(fishabm_ctx* c, int op, int nsteps) {
+    EnsembleArgs a;
+    memset(&a, 0, sizeof a);
+    const Buffers& b = c->buf[0];
+    a.rec = b.rec; a.cold0 = b.cold0; a.cold1 = b.cold1; a.quality = c->quality;
+    a.n = c->n; a.nx = c->g.nx_g; a.ny = c->g.ny; a.qcols = c->qcols; a.qcells = c->qrows * c->qcols;
+    a.replicates = c->R; a.replicate0 = c->p.replicate0;
+    a.op = op; a.nsteps = nsteps; a.step0 = c->step;
+    a.rolling = c->p.rolling; a.seed = c->p.seed; a.speed_norm = c->speed_norm;
+    a.cnt = c->cnt; a.turn = c->turn; a.aux = c->aux;
+    return a;
+}
+int ens_launch(fishabm_ctx* ctx, const EnsembleArgs& a) {
+    ensemble_kernel<<<ctx->R, ENS_THREADS, ctx->ens_smem, ctx->stream>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+int ens_timed(fishabm_ctx* ctx, int op, int nsteps) {
+    int rc;
+    if ((rc = begin_timed(ctx))) return rc;
+    if ((rc = ens_launch(ctx, ens_args(ctx, op, nsteps)))) return rc;
+    return end_timed(ctx);
+}
+int ens_query(fishabm_ctx* ctx, int32_t* cnt4, double* turn, int32_t* n_avoid, int32_t* n_align, int32_t* n_attract, double* speed) {
+    int rc;
+    if ((rc = ens_launch(ctx, ens_args(ctx, ENS_OP_QUERY, 0)))) return rc;
+    const long long tot = (long long)ctx->R * ctx->n;
+    EnsPassOutArgs o{ctx->cnt, ctx->turn, tot, ctx->speed_norm, cnt4 ? ctx->st_i4 : nullptr, turn ? ctx->st_dir : nullptr,
+                     n_avoid ? ctx->st_lag : nullptr, n_align ? ctx->st_rate : nullptr, n_attract ? ctx->st_intake : nullptr, speed ? ctx->st_sf : nullptr};
+    ens_export_pass_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(o);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    cudaStream_t s = ctx->stream;
+    if (cnt4) CK(cudaMemcpyAsync(cnt4, ctx->st_i4, 4 * tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (turn) CK(cudaMemcpyAsync(turn, ctx->st_dir, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (n_avoid) CK(cudaMemcpyAsync(n_avoid, ctx->st_lag, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (n_align) CK(cudaMemcpyAsync(n_align, ctx->st_rate, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (n_attract) CK(cudaMemcpyAsync(n_attract, ctx->st_intake, tot * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (speed) CK(cudaMemcpyAsync(speed, ctx->st_sf, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -380,8 +430,12 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (p->n < 1 || p->n >= (1 << 28)) return fail(nullptr, FISHABM_E_ARG, "n must be in [1, 2^28)");
     if (p->w % CELL_I || p->h % CELL_I || p->w < 3 * CELL_I || p->h < 3 * CELL_I)
         return fail(nullptr, FISHABM_E_ARG, "w and h must be multiples of 200 and at least 600 (got %d x %d)", p->w, p->h);
-    if (p->mode != FISHABM_MODE_CELL_FP32) return fail(nullptr, FISHABM_E_ARG, "mode %d is not available in this build", p->mode);
-    if (p->replicates != 1) return fail(nullptr, FISHABM_E_ARG, "replicates > 1: use the ensemble entry points (fishabm_ensemble_*)");
+    if (p->mode != FISHABM_MODE_CELL_FP32 && p->mode != FISHABM_MODE_ENSEMBLE) return fail(nullptr, FISHABM_E_ARG, "mode %d is not available in this build", p->mode);
+    if (p->replicates < 1) return fail(nullptr, FISHABM_E_ARG, "replicates must be >= 1");
+    const bool ens = p->replicates > 1 || p->mode == FISHABM_MODE_ENSEMBLE;
+    if (ens && (p->n > ENS_MAX_FISH || p->nranks != 1 || p->force_slab))
+        return fail(nullptr, FISHABM_E_ARG, "ensembles need n <= %d fish per school and no slabs (replicates shard across GPUs by replicate0)", ENS_MAX_FISH);
+    if (ens && (long long)p->replicates * p->n >= (1LL << 31)) return fail(nullptr, FISHABM_E_ARG, "replicates * n must stay below 2^31");
     if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(nullptr, FISHABM_E_ARG, "rank %d / nranks %d", p->rank, p->nranks);
     // a fish that migrates into a slab's last column must not at the same time be a ghost for the slab beyond it
     // (that slab's halo was packed before the migrant arrived): every slab needs two owned columns
@@ -400,6 +454,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     c->p = *p;
     c->n = p->n;
     const int nx_g = p->w / CELL_I, ny = p->h / CELL_I;
+    c->ens = ens;
+    c->R = p->replicates;
     c->slab = p->nranks > 1 || p->force_slab;
     c->col0 = (int)((long long)p->rank * nx_g / p->nranks);
     const int col1 = (int)((long long)(p->rank + 1) * nx_g / p->nranks);
@@ -429,12 +485,17 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     } else {
         c->cap = p->n;
     }
-    const size_t n = (size_t)c->n, cap = (size_t)c->cap, nq = (size_t)c->qrows * c->qcols;
+    if (ens) {
+        c->ens_smem = ensemble_smem_bytes(p->n, c->qrows * c->qcols);
+        if (c->ens_smem > 227 * 1024) { delete c; return fail(nullptr, FISHABM_E_ARG, "ensemble school does not fit in shared memory (%zu bytes): smaller n or window", c->ens_smem); }
+    }
+    // an ensemble reuses the single-school fields with R*n entries (one buffer set, no sort structures)
+    const size_t n = (size_t)c->n * c->R, cap = ens ? n : (size_t)c->cap, nq = (size_t)c->qrows * c->qcols * c->R;
     bool ok = true;
     auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; g_create_error = cudaGetErrorString(r); } };
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
-    for (int k = 0; k < 2 && ok; ++k) {
+    for (int k = 0; k < (ens ? 1 : 2) && ok; ++k) {
         A(dalloc(&c->buf[k].rec, cap)); A(dalloc(&c->buf[k].cold0, cap)); A(dalloc(&c->buf[k].cold1, cap)); A(dalloc(&c->buf[k].cell, cap));
     }
     A(dalloc(&c->next_cell, cap)); A(dalloc(&c->next_rank, cap));
@@ -444,7 +505,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->quality, nq));
     A(dalloc(&c->upd_count, 1)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
     A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 1)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
-    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1));
+    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
     if (c->slab) {
@@ -464,6 +525,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
             A(cudaMemset(c->in_left, 0, sizeof(SlabHeader))); A(cudaMemset(c->in_right, 0, sizeof(SlabHeader)));
         }
     }
+    if (ok && ens) A(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ens_smem));
     if (ok) {
         A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
@@ -476,7 +538,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");
     if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
-    c->h_q8 = (uint8_t*)malloc(nq > 0 ? nq : 1);
+    c->h_q8 = (uint8_t*)malloc((size_t)c->qrows * c->qcols > 0 ? (size_t)c->qrows * c->qcols : 1);
     if (!ok || !c->h_q8) {
         std::string msg = "device allocation failed: " + g_create_error;
         fishabm_destroy(c);
@@ -496,7 +558,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
-    cudaFree(c->n_unsorted); cudaFree(c->err);
+    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
     cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);
@@ -516,7 +578,7 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     CK(cudaSetDevice(ctx->p.device));
     if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     ctx->pending_sample = false;
-    const size_t n = (size_t)ctx->n;
+    const size_t n = (size_t)ctx->n * ctx->R;
     cudaStream_t s = ctx->stream;
     if (ctx->slab) {  // a fish may not outrun its halo: |step| = speed * speed_factor <= 3 * speed must stay below one cell
         for (size_t i = 0; i < n; ++i)
@@ -531,6 +593,19 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     CK(cudaMemcpyAsync(ctx->st_intake, food_intake, n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), s));
     CK(cudaMemsetAsync(ctx->err, 0, sizeof(int), s));
+    if (ctx->ens) {
+        const Buffers& b = ctx->buf[0];
+        EnsIoArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake, b.rec, b.cold0, b.cold1,
+                    (long long)n, ctx->g.nx_g, ctx->g.ny, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+        ens_ingest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+        ctx->launches += 1;
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, ctx->bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (bad) { ctx->have_state = false; return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: coordinates must be finite and inside [0,w] x [0,h]"); }
+        ctx->have_state = true;
+        return 0;
+    }
     CK(cudaMemsetAsync(ctx->cell_count, 0, ((size_t)ctx->ncell + 1) * sizeof(int), s));
     ctx->h_n = ctx->slab ? 0 : ctx->n;  // whole school: entry i = fish i; slab: entries are claimed
     CK(cudaMemcpyAsync(ctx->n_unsorted, &ctx->h_n, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -556,6 +631,26 @@ int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* spe
     int rc = need_state(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) {
+        const size_t n = (size_t)ctx->n * ctx->R;
+        cudaStream_t s = ctx->stream;
+        const Buffers& b = ctx->buf[0];
+        EnsIoArgs a{coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr, speed ? ctx->st_speed : nullptr, speed_factor ? ctx->st_sf : nullptr,
+                    lag ? ctx->st_lag : nullptr, sample_rate ? ctx->st_rate : nullptr, food_intake ? ctx->st_intake : nullptr, b.rec, b.cold0, b.cold1,
+                    (long long)n, ctx->g.nx_g, ctx->g.ny, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+        ens_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (speed) CK(cudaMemcpyAsync(speed, ctx->st_speed, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (speed_factor) CK(cudaMemcpyAsync(speed_factor, ctx->st_sf, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (lag) CK(cudaMemcpyAsync(lag, ctx->st_lag, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (sample_rate) CK(cudaMemcpyAsync(sample_rate, ctx->st_rate, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (food_intake) CK(cudaMemcpyAsync(food_intake, ctx->st_intake, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return 0;
+    }
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     int cnt = 0;
     if ((rc = owned_range(ctx, &cnt))) return rc;
@@ -584,13 +679,17 @@ int fishabm_initialize(fishabm_ctx* ctx, double speed) {
     if (!ctx) return FISHABM_E_ARG;
     // initialize(), fish_mod.cpp:183-206.  Tiny and one-off: the state is composed on the host from the same
     // counter-based streams the device uses, then ingested like any other state.
-    const int n = ctx->n;
-    std::vector<double> coords(2 * (size_t)n), dir(n), sp(n, speed), sf(n, 1.0);
+    const size_t n = (size_t)ctx->n * ctx->R;
+    std::vector<double> coords(2 * n), dir(n), sp(n, speed), sf(n, 1.0);
     std::vector<int32_t> z(n, 0);
-    for (int i = 0; i < n; ++i) {
-        dir[i] = (double)fishrng::draw(ctx->p.seed, 0, 0, (uint32_t)i, STREAM_RANDOMWALK, 0, -45, 45);
-        coords[2 * (size_t)i] = ctx->p.w / 2 + fishrng::draw(ctx->p.seed, 0, 0, (uint32_t)i, STREAM_INIT, 0, 0, 200) - 100;
-        coords[2 * (size_t)i + 1] = ctx->p.h / 2 + fishrng::draw(ctx->p.seed, 0, 1, (uint32_t)i, STREAM_INIT, 0, 0, 200) - 100;
+    for (int r = 0; r < ctx->R; ++r) {
+        const uint32_t rep = ctx->p.replicate0 + (uint32_t)r;
+        for (int f = 0; f < ctx->n; ++f) {
+            const size_t i = (size_t)r * ctx->n + f;
+            dir[i] = (double)fishrng::draw(ctx->p.seed, rep, 0, (uint32_t)f, STREAM_RANDOMWALK, 0, -45, 45);
+            coords[2 * i] = ctx->p.w / 2 + fishrng::draw(ctx->p.seed, rep, 0, (uint32_t)f, STREAM_INIT, 0, 0, 200) - 100;
+            coords[2 * i + 1] = ctx->p.h / 2 + fishrng::draw(ctx->p.seed, rep, 1, (uint32_t)f, STREAM_INIT, 0, 0, 200) - 100;
+        }
     }
     return fishabm_set_state(ctx, coords.data(), dir.data(), sp.data(), sf.data(), z.data(), z.data(), z.data());
 }
@@ -609,17 +708,22 @@ int fishabm_set_quality(fishabm_ctx* ctx, const int32_t* q, int32_t rows, int32_
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     CK(cudaMemcpyAsync(ctx->quality, ctx->h_q8, (size_t)rows * ctx->qcols, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->ens && ctx->R > 1) {  // every replicate starts from the same grid
+        const long long tot = (long long)rows * ctx->qcols * ctx->R;
+        ens_broadcast_quality_kernel<<<1184, 256, 0, ctx->stream>>>(ctx->quality, ctx->quality, rows * ctx->qcols, tot);
+        ctx->launches += 1;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 int fishabm_get_quality(fishabm_ctx* ctx, int32_t replicate, int32_t* q, int32_t rows, int32_t cols, int32_t row_stride) {
     if (!ctx || !q) return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: null argument");
-    if (replicate != 0 || rows != ctx->qrows || cols != ctx->qcols_g || row_stride < cols)
-        return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: grid is %d x %d, replicate 0", ctx->qrows, ctx->qcols_g);
+    if (replicate < 0 || replicate >= ctx->R || rows != ctx->qrows || cols != ctx->qcols_g || row_stride < cols)
+        return fail(ctx, FISHABM_E_ARG, "fishabm_get_quality: grid is %d x %d, replicates 0..%d", ctx->qrows, ctx->qcols_g, ctx->R - 1);
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
-    CK(cudaMemcpyAsync(ctx->h_q8, ctx->quality, (size_t)rows * ctx->qcols, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_q8, ctx->quality + (size_t)replicate * rows * ctx->qcols, (size_t)rows * ctx->qcols, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < rows; ++r)
         for (int c = 0; c < ctx->qcols; ++c) q[(size_t)r * row_stride + ctx->qcol0 + c] = ctx->h_q8[(size_t)r * ctx->qcols + c];
@@ -630,6 +734,14 @@ int fishabm_sum_quality(fishabm_ctx* ctx, int64_t* sums) {
     if (!ctx || !sums) return fail(ctx, FISHABM_E_ARG, "fishabm_sum_quality: null argument");
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    if (ctx->ens) {
+        ens_sum_quality_kernel<<<ctx->R, 256, 0, ctx->stream>>>(ctx->quality, ctx->qrows * ctx->qcols, ctx->d_sums);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(sums, ctx->d_sums, (size_t)ctx->R * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     CK(cudaMemsetAsync(ctx->stats + 4, 0, sizeof(unsigned long long), ctx->stream));
     sum_quality_kernel<<<296, 256, 0, ctx->stream>>>(ctx->quality, (size_t)ctx->qrows * ctx->qcols, ctx->stats + 4);
     ctx->launches += 1;
@@ -706,6 +818,7 @@ int fishabm_zone_counts(fishabm_ctx* ctx, int32_t* out4) {
     if (rc) return rc;
     if (!out4) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) return ens_query(ctx, out4, nullptr, nullptr, nullptr, nullptr, nullptr);
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, out4, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -716,6 +829,7 @@ int fishabm_social(fishabm_ctx* ctx, double* turn, int32_t* n_avoid, int32_t* n_
     if (rc) return rc;
     if (!turn) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) return ens_query(ctx, nullptr, turn, n_avoid, n_align, n_attract, nullptr);
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, nullptr, turn, n_avoid, n_align, n_attract, nullptr);
@@ -726,6 +840,7 @@ int fishabm_get_speed(fishabm_ctx* ctx, double* out) {
     if (rc) return rc;
     if (!out) return fail(ctx, FISHABM_E_ARG, "null argument");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) return ens_query(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, out);
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     if ((rc = neighbour_pass(ctx, -1, false, ctx->step, ctx->step, false))) return rc;
     return export_pass(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, out);
@@ -736,6 +851,7 @@ int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out) {
     if (rc) return rc;
     if (!out) return fail(ctx, FISHABM_E_ARG, "null argument");
     if (!(r <= 200.0) || fov_deg < 0 || fov_deg > 360) return fail(ctx, FISHABM_E_ARG, "fishabm_in_zone: needs r <= 200 and 0 <= fov <= 360");
+    if (ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_in_zone is not available for ensembles (use fishabm_zone_counts)");
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     int cnt = 0;
@@ -756,6 +872,7 @@ int fishabm_move(fishabm_ctx* ctx) {
     int rc = need_state(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) return ens_timed(ctx, ENS_OP_MOVE, 1);
     if ((rc = begin_timed(ctx))) return rc;
     if ((rc = flush_pending(ctx, true))) return rc;
     if ((rc = neighbour_pass(ctx, 0, false, ctx->step, ctx->step, true))) return rc;
@@ -767,6 +884,7 @@ int fishabm_sample(fishabm_ctx* ctx) {
     int rc = need_state(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) { rc = ens_timed(ctx, ENS_OP_SAMPLE, 1); if (!rc) ctx->step += 1; return rc; }
     if ((rc = begin_timed(ctx))) return rc;
     if (ctx->pending_sample) {  // the step's sample() is the pending one
         if ((rc = flush_pending(ctx, true))) return rc;
@@ -809,6 +927,7 @@ int fishabm_step(fishabm_ctx* ctx, int32_t nsteps) {
     if (rc) return rc;
     if (nsteps < 1) return fail(ctx, FISHABM_E_ARG, "nsteps must be >= 1");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) { rc = ens_timed(ctx, ENS_OP_STEPS, nsteps); if (!rc) ctx->step += (uint32_t)nsteps; return rc; }
     if ((rc = begin_timed(ctx))) return rc;
     if ((rc = step_untimed(ctx, nsteps))) return rc;
     return end_timed(ctx);
@@ -817,6 +936,7 @@ int fishabm_step(fishabm_ctx* ctx, int32_t nsteps) {
 int fishabm_flush(fishabm_ctx* ctx) {
     int rc = need_state(ctx);
     if (rc) return rc;
+    if (ctx->ens) { ctx->last_ms = 0.f; ctx->nb_events_used = 0; return 0; }  // an ensemble step completes inside the call
     CK(cudaSetDevice(ctx->p.device));
     if ((rc = begin_timed(ctx))) return rc;
     if ((rc = flush_pending(ctx, true))) return rc;
@@ -828,6 +948,28 @@ int fishabm_run_logged(fishabm_ctx* ctx, int32_t nsteps, int64_t* sumq, int32_t*
     if (rc) return rc;
     if (nsteps < 1) return fail(ctx, FISHABM_E_ARG, "nsteps must be >= 1");
     CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) {
+        // the whole logged run is ONE launch: the loggers' rows are written from shared memory as the steps go by
+        const int rows = (intake && intake_every > 0) ? (nsteps + intake_every - 1) / intake_every : 0;
+        long long* d_sumq = nullptr;
+        int* d_intake = nullptr;
+        const size_t sq = (size_t)nsteps * ctx->R, si = (size_t)rows * ctx->R * ctx->n;
+        if (sumq) CK(cudaMalloc(&d_sumq, sq * sizeof(long long)));
+        if (rows) { cudaError_t e = cudaMalloc(&d_intake, si * sizeof(int)); if (e != cudaSuccess) { cudaFree(d_sumq); return fail(ctx, FISHABM_E_NOMEM, "intake log: %s", cudaGetErrorString(e)); } }
+        EnsembleArgs a = ens_args(ctx, ENS_OP_STEPS, nsteps);
+        a.sumq = d_sumq; a.intake = d_intake; a.intake_every = rows ? intake_every : 0;
+        rc = begin_timed(ctx);
+        if (!rc) rc = ens_launch(ctx, a);
+        if (!rc) rc = end_timed(ctx);
+        cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+        if (!rc && sumq) e1 = cudaMemcpy(sumq, d_sumq, sq * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (!rc && rows) e2 = cudaMemcpy(intake, d_intake, si * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(d_sumq); cudaFree(d_intake);
+        if (rc) return rc;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(ctx, FISHABM_E_CUDA, "copying the logs back: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        ctx->step += (uint32_t)nsteps;
+        return 0;
+    }
     int rows = 0;
     for (int z = 0; z < nsteps; ++z) {
         ctx->nb_events_used = 0;
@@ -847,6 +989,7 @@ int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k) {
     if (rc) return rc;
     if (!ids || k < 0) return fail(ctx, FISHABM_E_ARG, "null argument");
     if (k > ctx->n) return fail(ctx, FISHABM_E_ARG, "fishabm_feed: at most n ids per call");
+    if (ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_feed is not available for ensembles");
     if (k == 0) return 0;
     CK(cudaSetDevice(ctx->p.device));
     { int rcf = flush_pending(ctx); if (rcf) return rcf; }

@@ -178,11 +178,13 @@ __device__ __forceinline__ float average_from_sums_f(long long x, long long y) {
     return atan2_fast((float)y, (float)x) * (180.f / PI_F);
 }
 
-// Per-fish end of the neighbour pass, shared by both kernel designs: social()'s selection (fish_mod.cpp:355-376),
+// Per-fish end of the neighbour pass, shared by every kernel design: social()'s selection (fish_mod.cpp:355-376),
 // averageturn (:379-408), the random walk (:372-374) and sample()'s feeding decision (:543-547).
 // s[6] = fixed-point cos/sin sums (avoid x,y; align x,y; attract x,y), exact integers.
-__device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k1, float fx, float fy, int n15, int n100, int n200,
-                                             int nfr, const long long* s, int ties) {
+struct FocalResult { int4 cnt; float turn; uint32_t aux; };
+__device__ __forceinline__ FocalResult focal_result(uint64_t seed, uint32_t replicate, uint32_t step_sample, uint32_t step_move, int do_sample,
+                                                    uint32_t id, int lag, int sample_rate, float fx, float fy, int n15, int n100, int n200,
+                                                    int nfr, const long long* s, int ties) {
     uint32_t aux = AUX_EVALUATED;
     const int n_av = n15, n_al = n100 - n15, n_at = n200 - n100;
     float turn;  // degrees
@@ -198,21 +200,136 @@ __device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k
     } else if (n_al > 0) turn = average_from_sums_f(s[2], s[3]);
     else if (n_at > 0) turn = average_from_sums_f(s[4], s[5]);
     else {
-        turn = (float)fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)k1.w, STREAM_RANDOMWALK, 0, -45, 45);
+        turn = (float)fishrng::draw(seed, replicate, step_move, id, STREAM_RANDOMWALK, 0, -45, 45);
         aux |= AUX_RANDOMWALK;
     }
     aux |= (uint32_t)min(ties, 127) << AUX_TIE_SHIFT;
-    if (a.do_sample && k1.x == 0) {  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
-        const int dr = fishrng::draw(a.seed, a.replicate, a.step_sample, (uint32_t)k1.w, STREAM_SAMPLE, 0, 0, 35);
+    if (do_sample && lag == 0) {  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
+        const int dr = fishrng::draw(seed, replicate, step_sample, id, STREAM_SAMPLE, 0, 0, 35);
         const bool alone = (n_av == 0 && n_al < 5);
-        if (k1.y > dr && !alone) {
+        if (sample_rate > dr && !alone) {
             const int fxl = min((int)fx / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)fy / FOOD_I, FOOD_PER_CELL - 1);
             aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
         }
     }
-    a.cnt[idx] = make_int4(n15, n100, n200, nfr);
-    a.turn[idx] = turn;
-    a.aux[idx] = aux;
+    FocalResult r;
+    r.cnt = make_int4(n15, n100, n200, nfr); r.turn = turn; r.aux = aux;
+    return r;
+}
+
+__device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k1, float fx, float fy, int n15, int n100, int n200,
+                                             int nfr, const long long* s, int ties) {
+    const FocalResult r = focal_result(a.seed, a.replicate, a.step_sample, a.step_move, a.do_sample, (uint32_t)k1.w, k1.x, k1.y, fx, fy,
+                                       n15, n100, n200, nfr, s, ties);
+    a.cnt[idx] = r.cnt;
+    a.turn[idx] = r.turn;
+    a.aux[idx] = r.aux;
+}
+
+// One candidate pair, one lane: exact classification (with the fp64 re-check of borderline predicates), zone / front
+// counts, and the avoidance / alignment / attraction turn of the pair (fish_mod.cpp:316-351) added as fixed-point
+// cos/sin to the lane's partial sums.  (qx,qy) is the candidate already shifted into the focal cell's frame, (qc,qs) its
+// heading.  `raw(rx, ry, kcode)` yields the candidate's unshifted in-cell offset and its stencil code for the re-check;
+// `ids(my, nb)` yields the two fish ids for a tie draw.  Returns true when the pair was re-checked in fp64.
+struct PairAcc { int n15, n100, n200, nfr, ties; int ax0, ay0, ax1, ay1, ax2, ay2; };
+__device__ __forceinline__ void pair_acc_clear(PairAcc& A) { A.n15 = A.n100 = A.n200 = A.nfr = A.ties = 0; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0; }
+
+template <class Raw, class Ids>
+__device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float fc, float fs, float fdir, bool exotic, float qx, float qy,
+                                          float qc, float qs, uint64_t seed, uint32_t replicate, uint32_t step_move, const Raw& raw,
+                                          const Ids& ids, PairAcc& A) {
+    const float dx = qx - fx, dy = qy - fy;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    // d2 == 0: the fish itself or a coincident fish: acos(0/0) is NaN in the reference, the pair is dropped from every
+    // count (fish_mod.cpp:252-254)
+    live = live && (d2 > 0.f);
+    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+    const float d = d2 * rinv;
+    const float dot = fmaf(fc, dx, fs * dy);
+    const float ca = dot * rinv;
+    // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
+    const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
+    bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
+    unc = (unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb) && live;
+    bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
+    if (unc) {
+        float rx, ry; int kcode;
+        raw(rx, ry, kcode);
+        const unsigned bits = exact_pair_bits(fx, fy, fdir, rx, ry, kcode);
+        in15 = bits & 1u; in100 = bits & 2u; in200 = bits & 4u; vis = bits & 8u; front = bits & 16u;
+    }
+    const bool inter = live && vis && in200;
+    A.nfr += (live && front && in200) ? 1 : 0;
+    A.n200 += inter ? 1 : 0;
+    A.n100 += (inter && in100) ? 1 : 0;
+    A.n15 += (inter && in15) ? 1 : 0;
+    if (inter) {
+        const bool al = in100 && !in15;
+        const float cross = fmaf(fc, dy, -fs * dx);
+        const float crossA = fmaf(fc, qs, -fs * qc);
+        const float dotA = fmaf(fc, qc, fs * qs);
+        float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
+        bool tie180 = fabsf(beta) >= PI_F;
+        if (exotic) { beta = getangle_wrap_exotic(beta, fdir); tie180 = (beta == PI_F); }
+        float t = beta;
+        if (in15) {
+            t = beta - copysignf(PI_F, beta);
+            if (beta == 0.f) {  // dead ahead: +-180 at random (fish_mod.cpp:327-329), keyed by the neighbour's id
+                uint32_t my, nb;
+                ids(my, nb);
+                t = (fishrng::draw(seed, replicate, step_move, my, STREAM_CHOICE, nb, 0, 1) ? PI_F : -PI_F);
+                A.ties++;
+            }
+        } else if (al && tie180) {  // exactly opposite heading (fish_mod.cpp:460-462)
+            uint32_t my, nb;
+            ids(my, nb);
+            t = (fishrng::draw(seed, replicate, step_move, my, STREAM_CHOICE, nb, 0, 1) ? PI_F : -PI_F);
+            A.ties++;
+        }
+        const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
+        const float kz = in15 ? 0.1f : 0.004f;
+        const float wgt = __fdividef(1.f, fmaf(kz * ee, ee, 2.f));
+        const float th = t * wgt;
+        float sn, cs;
+        __sincosf(th, &sn, &cs);
+        const int vx = __float_as_int(cs + FIX_MAGIC) - FIX_MAGIC_BITS;
+        const int vy = __float_as_int(sn + FIX_MAGIC) - FIX_MAGIC_BITS;
+        if (in15) { A.ax0 += vx; A.ay0 += vy; }
+        else if (al) { A.ax1 += vx; A.ay1 += vy; }
+        else { A.ax2 += vx; A.ay2 += vy; }
+    }
+    return unc;
+}
+
+// move() for one fish (fish_mod.cpp:165-179) in cell/offset form.  In: record, cold state, cell (cx,cy), social turn,
+// front count, the error draw.  Out: the new record / heading / speed_factor and the UNWRAPPED new cell (the caller
+// applies the world's periodicity).
+__device__ __forceinline__ void move_core(float4& r, float4& c0, int lag, int& cx, int& cy, float turn, int front, int err, int rolling,
+                                          double speed_norm) {
+    double dir = (double)c0.x;
+    if (lag == 0) {
+        double d0 = dir;
+        if (d0 < 0) d0 += 360.0; else if (d0 >= 360.0) d0 -= 360.0;  // correctangle, :410-418
+        dir = d0 + ((double)turn + (double)err);
+        double sn, cs;
+        sincospi(dir / 180.0, &sn, &cs);
+        const double stepl = (double)c0.y * (double)c0.z;  // speed * OLD speed_factor (:171-172)
+        const double px = (double)r.x + stepl * cs, py = (double)r.y + stepl * sn;
+        if (rolling) c0.z = (float)(1.0 + 2.0 * (double)front / speed_norm);  // get_speed, :588-591
+        // periodic wrap (correct_coords, :466-480) in cell/offset form
+        const double kx = floor(px / (double)CELL_I), ky = floor(py / (double)CELL_I);
+        float ox = (float)(px - kx * CELL_I), oy = (float)(py - ky * CELL_I);
+        cx += (int)kx; cy += (int)ky;
+        if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
+        if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
+        r.x = ox; r.y = oy;
+    } else {
+        dir = dir + (double)err;  // :177-179
+    }
+    c0.x = (float)dir;
+    double sn, cs;
+    sincospi((double)c0.x / 180.0, &sn, &cs);
+    r.z = (float)cs; r.w = (float)sn;
 }
 
 template <bool STATS>
@@ -487,34 +604,12 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     if (a.do_move) {  // move(), fish_mod.cpp:165-179
         const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -10, 10);
         float4 r = a.rec[i];
-        double dir = (double)c0.x;
         int cx = mycell / ny, cy = mycell % ny;
-        if (c1.x == 0) {
-            double d0 = dir;
-            if (d0 < 0) d0 += 360.0; else if (d0 >= 360.0) d0 -= 360.0;  // correctangle, :410-418
-            dir = d0 + ((double)a.turn[i] + (double)err);
-            double sn, cs;
-            sincospi(dir / 180.0, &sn, &cs);
-            const double stepl = (double)c0.y * (double)c0.z;  // speed * OLD speed_factor (:171-172)
-            double px = (double)r.x + stepl * cs, py = (double)r.y + stepl * sn;
-            if (a.rolling) c0.z = (float)(1.0 + 2.0 * (double)a.cnt[i].w / a.speed_norm);  // get_speed, :588-591
-            // periodic wrap (correct_coords, :466-480) in cell/offset form
-            const double kx = floor(px / (double)CELL_I), ky = floor(py / (double)CELL_I);
-            float ox = (float)(px - kx * CELL_I), oy = (float)(py - ky * CELL_I);
-            cx += (int)kx; cy += (int)ky;
-            if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
-            if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
-            if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
-            else if (cx < 0 || cx >= a.g.lnx) { atomicOr(a.err, ERR_STEP_TOO_LONG); cx = max(0, min(cx, a.g.lnx - 1)); }
-            cy %= ny; if (cy < 0) cy += ny;
-            r.x = ox; r.y = oy;
-        } else {
-            dir = dir + (double)err;  // :177-179
-        }
-        c0.x = (float)dir;
-        double sn, cs;
-        sincospi((double)c0.x / 180.0, &sn, &cs);
-        r.z = (float)cs; r.w = (float)sn;
+        const bool moving = c1.x == 0;
+        move_core(r, c0, c1.x, cx, cy, moving ? a.turn[i] : 0.f, moving ? a.cnt[i].w : 0, err, a.rolling, a.speed_norm);
+        if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
+        else if (cx < 0 || cx >= a.g.lnx) { atomicOr(a.err, ERR_STEP_TOO_LONG); cx = max(0, min(cx, a.g.lnx - 1)); }
+        cy %= ny; if (cy < 0) cy += ny;
         const int newcell = cx * ny + cy;
         a.rec[i] = r;
         a.next_cell[i] = newcell;
@@ -706,11 +801,11 @@ struct ScatterArgs {
     const float4* rec_in; const float4* cold0_in; const int4* cold1_in;
     float4* rec_out; float4* cold0_out; int4* cold1_out; int* cell_out;
     const int* next_cell; const int* next_rank; const int* start;
-    const int* n_unsorted;
+    const int* n_unsorted; int cap;
 };
 __global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *a.n_unsorted) return;
+    if (i >= min(*a.n_unsorted, a.cap)) return;  // claims beyond the capacity were refused (and reported)
     const int c = a.next_cell[i];
     if (c < 0) return;  // last step's ghost
     const int dst = a.start[c] + a.next_rank[i];

@@ -147,76 +147,28 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                     // ---- process (compacted pairs, one per lane, same focal fish in every lane)
                     const float fdir = S.fdir[f];
                     const bool exotic = fabsf(fdir) >= 540.f;
-                    int ax0 = 0, ay0 = 0, ax1 = 0, ay1 = 0, ax2 = 0, ay2 = 0;
-                    int n15 = 0, n100 = 0, n200 = 0, nfr = 0, ties = 0;
+                    PairAcc P;
+                    pair_acc_clear(P);
                     for (int q0 = 0; q0 < qn; q0 += 32) {
                         const int e = q0 + lane;
-                        bool live = e < qn;
+                        const bool live = e < qn;
                         const int j = live ? (int)S.queue[e] : 0;
-                        const float qx = S.wx[j], qy = S.wy[j];
-                        const float dx = qx - fx, dy = qy - fy;
-                        const float d2 = fmaf(dx, dx, dy * dy);
-                        // d2 == 0: the fish itself or a coincident fish: acos(0/0) is NaN in the reference, the pair is
-                        // dropped from every count (fish_mod.cpp:252-254)
-                        live = live && (d2 > 0.f);
-                        const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
-                        const float d = d2 * rinv;
-                        const float dot = fmaf(fc, dx, fs * dy);
-                        const float ca = dot * rinv;
-                        const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
-                        bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
-                        unc = (unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb) && live;
-                        bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
-                        if (unc) {
-                            const uint32_t code = S.wcode[j];
-                            const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
-                            const unsigned bits = exact_pair_bits(fx, fy, fdir, raw.x, raw.y, (int)(code >> 28));
-                            in15 = bits & 1u; in100 = bits & 2u; in200 = bits & 4u; vis = bits & 8u; front = bits & 16u;
-                        }
+                        const bool unc = pair_math(
+                            live, fx, fy, fc, fs, fdir, exotic, S.wx[j], S.wy[j], S.wc[j], S.ws[j], a.seed, a.replicate, a.step_move,
+                            [&](float& rx, float& ry, int& kcode) {
+                                const uint32_t code = S.wcode[j];
+                                const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
+                                rx = raw.x; ry = raw.y; kcode = (int)(code >> 28);
+                            },
+                            [&](uint32_t& my, uint32_t& nb) {
+                                nb = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
+                                my = (uint32_t)a.cold1[S.fidx[f]].w;
+                            },
+                            P);
                         if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
-                        const bool inter = live && vis && in200;
-                        nfr += (live && front && in200) ? 1 : 0;
-                        n200 += inter ? 1 : 0;
-                        n100 += (inter && in100) ? 1 : 0;
-                        n15 += (inter && in15) ? 1 : 0;
-                        if (inter) {
-                            // ---- turn contribution of this neighbour (fish_mod.cpp:316-351), radians
-                            const bool al = in100 && !in15;
-                            const float qc = S.wc[j], qs = S.ws[j];
-                            const float cross = fmaf(fc, dy, -fs * dx);
-                            const float crossA = fmaf(fc, qs, -fs * qc);
-                            const float dotA = fmaf(fc, qc, fs * qs);
-                            float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
-                            bool tie180 = fabsf(beta) >= PI_F;
-                            if (exotic) { beta = getangle_wrap_exotic(beta, fdir); tie180 = (beta == PI_F); }
-                            float t = beta;
-                            if (in15) {
-                                t = beta - copysignf(PI_F, beta);
-                                if (beta == 0.f) {  // dead ahead: +-180 at random (fish_mod.cpp:327-329), keyed by the neighbour's id
-                                    const uint32_t nid = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
-                                    const uint32_t myid = (uint32_t)a.cold1[S.fidx[f]].w;
-                                    t = (fishrng::draw(a.seed, a.replicate, a.step_move, myid, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
-                                    ties++;
-                                }
-                            } else if (al && tie180) {  // exactly opposite heading (fish_mod.cpp:460-462)
-                                const uint32_t nid = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
-                                const uint32_t myid = (uint32_t)a.cold1[S.fidx[f]].w;
-                                t = (fishrng::draw(a.seed, a.replicate, a.step_move, myid, STREAM_CHOICE, nid, 0, 1) ? PI_F : -PI_F);
-                                ties++;
-                            }
-                            const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
-                            const float kz = in15 ? 0.1f : 0.004f;
-                            const float wgt = __fdividef(1.f, fmaf(kz * ee, ee, 2.f));
-                            const float th = t * wgt;
-                            float sn, cs;
-                            __sincosf(th, &sn, &cs);
-                            const int vx = __float_as_int(cs + FIX_MAGIC) - FIX_MAGIC_BITS;
-                            const int vy = __float_as_int(sn + FIX_MAGIC) - FIX_MAGIC_BITS;
-                            if (in15) { ax0 += vx; ay0 += vy; }
-                            else if (al) { ax1 += vx; ay1 += vy; }
-                            else { ax2 += vx; ay2 += vy; }
-                        }
                     }
+                    const int ax0 = P.ax0, ay0 = P.ay0, ax1 = P.ax1, ay1 = P.ay1, ax2 = P.ax2, ay2 = P.ay2;
+                    const int n15 = P.n15, n100 = P.n100, n200 = P.n200, nfr = P.nfr, ties = P.ties;
                     // ---- reduce the lanes' partial sums; lane 0 owns the focal fish's accumulators
                     const int r0 = __reduce_add_sync(FULL, ax0), r1 = __reduce_add_sync(FULL, ay0);
                     const int r2 = __reduce_add_sync(FULL, ax1), r3 = __reduce_add_sync(FULL, ay1);

@@ -26,15 +26,19 @@ class School:
     def __init__(self, n: int = 60, w: int = 2000, h: int = 2000, seed: int = 0, device: int = 0,
                  rolling: bool = True, speed_norm: float = 0.0, mode: int = _lib.MODE_CELL_FP32,
                  rank: int = 0, nranks: int = 1, force_slab: bool = False, capacity: int = 0, halo_capacity: int = 0,
-                 migrant_capacity: int = 0):
+                 migrant_capacity: int = 0, replicates: int = 1, replicate0: int = 0):
         """rank / nranks > 1: this context is one x-slab of the school (see include/fishabm.h and slab.py); n, w, h and
-        every array passed in or out still describe the WHOLE school."""
+        every array passed in or out still describe the WHOLE school.
+        replicates > 1 (or mode=MODE_ENSEMBLE): an ensemble of independent schools; arrays are flat, replicates*n
+        entries, replicate-major (class Ensemble reshapes them)."""
         self.L = _lib.load()
         p = _lib.Params()
         self.L.fishabm_params_default(C.byref(p))
         p.n, p.w, p.h, p.seed, p.device, p.rolling, p.speed_norm, p.mode = n, w, h, seed, device, int(rolling), speed_norm, mode
         p.rank, p.nranks, p.force_slab = rank, nranks, int(force_slab)
         p.capacity, p.halo_capacity, p.migrant_capacity = capacity, halo_capacity, migrant_capacity
+        p.replicates, p.replicate0 = replicates, replicate0
+        self.replicates = replicates
         self.is_slab = nranks > 1 or force_slab
         self.params = p
         self.ctx = C.c_void_p()
@@ -42,6 +46,7 @@ class School:
         if rc != 0:
             raise FishAbmError(rc, self.L.fishabm_last_error(None).decode())
         self.n, self.w, self.h = n, w, h
+        self.total = n * replicates
         self.rows, self.cols = h // 20, w // 20
 
     def close(self):
@@ -71,7 +76,7 @@ class School:
         i = lambda a: np.ascontiguousarray(a, np.int32)
         coords, dir, speed, speed_factor = f(coords).reshape(-1, 2), f(dir), f(speed), f(speed_factor)
         lag, sample_rate, food_intake = i(lag), i(sample_rate), i(food_intake)
-        assert coords.shape[0] == dir.shape[0] == self.n
+        assert coords.shape[0] == dir.shape[0] == self.total
         self._ck(self.L.fishabm_set_state(self.ctx, _p(coords), _p(dir), _p(speed), _p(speed_factor), _p(lag),
                                           _p(sample_rate), _p(food_intake)))
 
@@ -80,7 +85,7 @@ class School:
     def get_state(self) -> dict:
         """Whole school: every fish.  Slab: only the entries of the fish this slab owns are written; the others keep
         NaN / NOT_OWNED (see owned_mask)."""
-        n = self.n
+        n = self.total
         out = dict(coords=np.empty((n, 2)), dir=np.empty(n), speed=np.empty(n), speed_factor=np.empty(n),
                    lag=np.empty(n, np.int32), sample_rate=np.empty(n, np.int32), food_intake=np.empty(n, np.int32))
         if self.is_slab:
@@ -103,17 +108,17 @@ class School:
         q = np.ascontiguousarray(q, np.int32)
         self._ck(self.L.fishabm_set_quality(self.ctx, _p(q), q.shape[0], q.shape[1], q.shape[1]))
 
-    def get_quality(self) -> np.ndarray:
+    def get_quality(self, replicate: int = 0) -> np.ndarray:
         """Whole school: the grid.  Slab: the owned columns, -1 elsewhere."""
         q = np.full((self.rows, self.cols), -1, np.int32)
-        self._ck(self.L.fishabm_get_quality(self.ctx, 0, _p(q), self.rows, self.cols, self.cols))
+        self._ck(self.L.fishabm_get_quality(self.ctx, replicate, _p(q), self.rows, self.cols, self.cols))
         return q
 
-    def sum_array(self) -> int:
-        """sum_array(quality, struc), fish_mod.cpp:593-601"""
-        s = np.zeros(1, np.int64)
+    def sum_array(self):
+        """sum_array(quality, struc), fish_mod.cpp:593-601 (one value per replicate for an ensemble)"""
+        s = np.zeros(self.replicates, np.int64)
         self._ck(self.L.fishabm_sum_quality(self.ctx, _p(s)))
-        return int(s[0])
+        return int(s[0]) if self.replicates == 1 else s
 
     def get_environment(self, path: str):
         """get_environment(environment, quality, struc), fish_mod.cpp:603-629 (the CSV parse; painting is viewer-only)"""
@@ -127,23 +132,23 @@ class School:
 
     # ---- frozen-state queries --------------------------------------------------------------------------------
     def in_zone(self, fov: int, r: float) -> np.ndarray:
-        out = np.full(self.n, -1, np.int32)
+        out = np.full(self.total, -1, np.int32)
         self._ck(self.L.fishabm_in_zone(self.ctx, int(fov), float(r), _p(out)))
         return out
 
     def zone_counts(self) -> np.ndarray:
-        out = np.full((self.n, 4), -1, np.int32)
+        out = np.full((self.total, 4), -1, np.int32)
         self._ck(self.L.fishabm_zone_counts(self.ctx, _p(out)))
         return out
 
     def social(self):
-        turn = np.full(self.n, np.nan)
-        na, nl, nt = (np.full(self.n, -1, np.int32) for _ in range(3))
+        turn = np.full(self.total, np.nan)
+        na, nl, nt = (np.full(self.total, -1, np.int32) for _ in range(3))
         self._ck(self.L.fishabm_social(self.ctx, _p(turn), _p(na), _p(nl), _p(nt)))
         return turn, na, nl, nt
 
     def get_speed(self) -> np.ndarray:
-        out = np.full(self.n, np.nan)
+        out = np.full(self.total, np.nan)
         self._ck(self.L.fishabm_get_speed(self.ctx, _p(out)))
         return out
 
@@ -166,9 +171,11 @@ class School:
         self._ck(self.L.fishabm_feed(self.ctx, _p(ids), len(ids)))
 
     def run_logged(self, nsteps: int, log_sumq: bool = True, intake_every: int = 0):
-        sumq = np.zeros(nsteps, np.int64) if log_sumq else None
+        """the reference's two commented-out loggers (fish_mod.cpp:132-141,149-154): sum_array after every step
+        ([nsteps] or [nsteps, replicates]) and food_intake every `intake_every` steps ([rows, replicates*n])"""
+        sumq = (np.zeros((nsteps, self.replicates), np.int64) if self.replicates > 1 else np.zeros(nsteps, np.int64)) if log_sumq else None
         rows = (nsteps + intake_every - 1) // intake_every if intake_every > 0 else 0
-        intake = np.zeros((rows, self.n), np.int32) if rows else None
+        intake = np.zeros((rows, self.total), np.int32) if rows else None
         self._ck(self.L.fishabm_run_logged(self.ctx, nsteps, _p(sumq), _p(intake), intake_every))
         return sumq, intake
 
@@ -233,6 +240,38 @@ class School:
         nbytes = C.c_int64(0)
         self._ck(self.L.fishabm_slab_buffers(self.ctx, *(C.byref(p) for p in ptrs), C.byref(nbytes)))
         return tuple(p.value for p in ptrs), int(nbytes.value)
+
+
+class Ensemble(School):
+    """replicates independent schools of n fish (BASELINE.json configs[4]); per-fish arrays are [replicates, n]"""
+
+    def __init__(self, replicates: int, n: int = 200, **kw):
+        super().__init__(n=n, replicates=replicates, mode=_lib.MODE_ENSEMBLE, **kw)
+
+    def set_state(self, coords, dir, speed, speed_factor, lag, sample_rate, food_intake):
+        r = lambda a: np.asarray(a).reshape(self.total, *np.asarray(a).shape[2:])
+        super().set_state(r(coords), r(dir), r(speed), r(speed_factor), r(lag), r(sample_rate), r(food_intake))
+
+    def get_state(self) -> dict:
+        g = super().get_state()
+        return {k: v.reshape(self.replicates, self.n, *v.shape[1:]) for k, v in g.items()}
+
+    def zone_counts(self):
+        return super().zone_counts().reshape(self.replicates, self.n, 4)
+
+    def social(self):
+        return tuple(a.reshape(self.replicates, self.n) for a in super().social())
+
+    def get_speed(self):
+        return super().get_speed().reshape(self.replicates, self.n)
+
+    def run_logged(self, nsteps: int, log_sumq: bool = True, intake_every: int = 0):
+        sumq, intake = super().run_logged(nsteps, log_sumq, intake_every)
+        if sumq is not None:
+            sumq = sumq.reshape(nsteps, self.replicates)
+        if intake is not None:
+            intake = intake.reshape(-1, self.replicates, self.n)
+        return sumq, intake
 
 
 def slab_unique_id() -> bytes:

@@ -44,7 +44,9 @@ enum {
 enum {
     FISHABM_MODE_CELL_FP32 = 0,  /* product path: cell list + fused fp32 neighbour kernel with fp64 re-check
                                     of borderline predicates */
-    FISHABM_MODE_BRUTE_FP64 = 1  /* check mode: all-pairs, fp64, candidate order = id order, literal restatement */
+    FISHABM_MODE_BRUTE_FP64 = 1, /* check mode: all-pairs, fp64, candidate order = id order, literal restatement (not built) */
+    FISHABM_MODE_ENSEMBLE = 2    /* replicate ensemble: one CTA per school, all pairs in shared memory; implied by
+                                    replicates > 1, may be forced for a single school (n <= 1024) */
 };
 
 /* random streams = the reference's distributions (fish_mod.cpp:28-33) */
@@ -62,7 +64,10 @@ typedef struct fishabm_params {
                               at least 600 in cell-list mode */
     int32_t mode;          /* FISHABM_MODE_* */
     int32_t device;        /* CUDA device ordinal */
-    int32_t replicates;    /* 1 = one school; >1 = ensemble of independent schools of n fish (w,h = 2000 window each) */
+    int32_t replicates;    /* 1 = one school; >1 = ensemble of independent schools of n <= 1024 fish, each in its own
+                              w x h window with its own food grid.  Arrays then hold replicates*n entries,
+                              replicate-major.  fishabm_in_zone (arbitrary fov/r) and fishabm_feed are not available
+                              for ensembles; fishabm_step completes its last sample() inside the call. */
     int32_t rolling;       /* 1 = get_speed active (the committed reference, fish_mod.cpp:173); 0 = speed_factor only
                               changes through feed() (the "non-rolling" variant of data/norolling_*) */
     uint64_t seed;         /* Philox key; draws are addressed by (seed, replicate, step, fish id, stream, k) */
@@ -74,6 +79,8 @@ typedef struct fishabm_params {
                               (0 = automatic: 1.3 x the uniform-density expectation) */
     int32_t halo_capacity;    /* ghosts per slab message (0 = automatic: 2 x fish per cell column + 4096) */
     int32_t migrant_capacity; /* migrants per slab message (0 = automatic) */
+    uint32_t replicate0;   /* replicate id of the (first) school: part of the Philox key, so that an ensemble sharded
+                              across GPUs, or one school of it run alone, draws the same numbers */
     int32_t force_slab;    /* 1 = use halo columns and the message path even with nranks == 1 (the slab is then its own
                               neighbour); for testing the decomposition on one GPU */
 } fishabm_params;
