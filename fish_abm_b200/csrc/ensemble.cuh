@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(ENS_THREADS) ensemble_kernel(const EnsembleArg
             const long long sums[6] = {(long long)__reduce_add_sync(FULL, P.ax0), (long long)__reduce_add_sync(FULL, P.ay0),
                                        (long long)__reduce_add_sync(FULL, P.ax1), (long long)__reduce_add_sync(FULL, P.ay1),
                                        (long long)__reduce_add_sync(FULL, P.ax2), (long long)__reduce_add_sync(FULL, P.ay2)};
-            const int c15 = __reduce_add_sync(FULL, P.n15), c100 = __reduce_add_sync(FULL, P.n100);
-            const int c200 = __reduce_add_sync(FULL, P.n200), cfr = __reduce_add_sync(FULL, P.nfr);
+            const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
+            const int c200 = cfar & 0xFFFF, cfr = cfar >> 16, c100 = cnear & 0xFFFF, c15 = cnear >> 16;
             const int ties = __reduce_add_sync(FULL, P.ties);
             if (lane == 0) {
                 const FocalResult r = focal_result(a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,

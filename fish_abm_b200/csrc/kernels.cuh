@@ -85,11 +85,16 @@ constexpr uint32_t AUX_RANDOMWALK = 1u << 8;  // turn came from the random-walk 
 constexpr uint32_t AUX_TIE_SHIFT = 9;         // tie-break draws consumed (saturating 7 bits)
 constexpr uint32_t AUX_EVALUATED = 1u << 16;  // the fish was active in this pass
 
+// MUFU.RSQ / MUFU.RCP without the denormal fix-up code nvcc wraps around rsqrtf / __fdividef (three extra
+// instructions each); identical results for normal arguments, and every argument here is >= 1e-37.
+__device__ __forceinline__ float rsqrt_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // atan2 in radians, result in (-pi, pi]; max abs error ~1.5e-7 rad.  (0,0) -> 0.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float t = __fdividef(mn, fmaxf(mx, 1e-37f));
+    const float t = mn * rcp_ftz(fmaxf(mx, 1e-37f));
     const float s = t * t;
     float p = -4.054543159e-03f;
     p = fmaf(p, s, 2.186286711e-02f);
@@ -231,8 +236,10 @@ __device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k
 // cos/sin to the lane's partial sums.  (qx,qy) is the candidate already shifted into the focal cell's frame, (qc,qs) its
 // heading.  `raw(rx, ry, kcode)` yields the candidate's unshifted in-cell offset and its stencil code for the re-check;
 // `ids(my, nb)` yields the two fish ids for a tie draw.  Returns true when the pair was re-checked in fp64.
-struct PairAcc { int n15, n100, n200, nfr, ties; int ax0, ay0, ax1, ay1, ax2, ay2; };
-__device__ __forceinline__ void pair_acc_clear(PairAcc& A) { A.n15 = A.n100 = A.n200 = A.nfr = A.ties = 0; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0; }
+// counts are packed two to a word (16 bits each: a lane sees at most 32 candidates per reduction, a warp 1024):
+//   c_far = n200 | front << 16,  c_near = n100 | n15 << 16
+struct PairAcc { int c_far, c_near, ties; int ax0, ay0, ax1, ay1, ax2, ay2; };
+__device__ __forceinline__ void pair_acc_clear(PairAcc& A) { A.c_far = A.c_near = A.ties = 0; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0; }
 
 template <class Raw, class Ids>
 __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float fc, float fs, float fdir, bool exotic, float qx, float qy,
@@ -243,14 +250,15 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     // d2 == 0: the fish itself or a coincident fish: acos(0/0) is NaN in the reference, the pair is dropped from every
     // count (fish_mod.cpp:252-254)
     live = live && (d2 > 0.f);
-    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+    const float rinv = rsqrt_ftz(fmaxf(d2, 1e-30f));
     const float d = d2 * rinv;
     const float dot = fmaf(fc, dx, fs * dy);
     const float ca = dot * rinv;
     // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
     const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
-    bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
-    unc = (unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb) && live;
+    const float near_r = fminf(fminf(fabsf(d - 15.f), fabsf(d - 100.f)), fabsf(d - 200.f));
+    const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
+    const bool unc = (near_r < BAND_R || near_c < tb) && live;
     bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
     if (unc) {
         float rx, ry; int kcode;
@@ -259,10 +267,8 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
         in15 = bits & 1u; in100 = bits & 2u; in200 = bits & 4u; vis = bits & 8u; front = bits & 16u;
     }
     const bool inter = live && vis && in200;
-    A.nfr += (live && front && in200) ? 1 : 0;
-    A.n200 += inter ? 1 : 0;
-    A.n100 += (inter && in100) ? 1 : 0;
-    A.n15 += (inter && in15) ? 1 : 0;
+    A.c_far += (inter ? 1 : 0) + ((live && front && in200) ? 0x10000 : 0);
+    A.c_near += inter ? ((in100 ? 1 : 0) + (in15 ? 0x10000 : 0)) : 0;
     if (inter) {
         const bool al = in100 && !in15;
         const float cross = fmaf(fc, dy, -fs * dx);
@@ -288,7 +294,7 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
         }
         const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
         const float kz = in15 ? 0.1f : 0.004f;
-        const float wgt = __fdividef(1.f, fmaf(kz * ee, ee, 2.f));
+        const float wgt = rcp_ftz(fmaf(kz * ee, ee, 2.f));
         const float th = t * wgt;
         float sn, cs;
         __sincosf(th, &sn, &cs);

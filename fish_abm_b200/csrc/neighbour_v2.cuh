@@ -167,15 +167,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                             P);
                         if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
                     }
-                    const int ax0 = P.ax0, ay0 = P.ay0, ax1 = P.ax1, ay1 = P.ay1, ax2 = P.ax2, ay2 = P.ay2;
-                    const int n15 = P.n15, n100 = P.n100, n200 = P.n200, nfr = P.nfr, ties = P.ties;
                     // ---- reduce the lanes' partial sums; lane 0 owns the focal fish's accumulators
-                    const int r0 = __reduce_add_sync(FULL, ax0), r1 = __reduce_add_sync(FULL, ay0);
-                    const int r2 = __reduce_add_sync(FULL, ax1), r3 = __reduce_add_sync(FULL, ay1);
-                    const int r4 = __reduce_add_sync(FULL, ax2), r5 = __reduce_add_sync(FULL, ay2);
-                    const int c15 = __reduce_add_sync(FULL, n15), c100 = __reduce_add_sync(FULL, n100);
-                    const int c200 = __reduce_add_sync(FULL, n200), cfr = __reduce_add_sync(FULL, nfr);
-                    const int tsum = __reduce_add_sync(FULL, ties);
+                    const int r0 = __reduce_add_sync(FULL, P.ax0), r1 = __reduce_add_sync(FULL, P.ay0);
+                    const int r2 = __reduce_add_sync(FULL, P.ax1), r3 = __reduce_add_sync(FULL, P.ay1);
+                    const int r4 = __reduce_add_sync(FULL, P.ax2), r5 = __reduce_add_sync(FULL, P.ay2);
+                    const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
+                    const int c200 = cfar & 0xFFFF, cfr = cfar >> 16, c100 = cnear & 0xFFFF, c15 = cnear >> 16;
+                    const int tsum = __any_sync(FULL, P.ties != 0) ? __reduce_add_sync(FULL, P.ties) : 0;
                     if (STATS) st_inter += (unsigned)c200;
                     if (lane == 0) {
                         if (first_batch) {
