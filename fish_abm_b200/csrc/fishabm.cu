@@ -532,8 +532,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     }
     if (ok) {
         int per_sm = 0, sms = 0;
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
         c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");

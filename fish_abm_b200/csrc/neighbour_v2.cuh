@@ -1,18 +1,23 @@
-// K4, second design: candidate-parallel neighbour kernel.
+// K4, second design (default): candidate-parallel neighbour kernel.
 //
-// One warp owns one focal cell.  The <= 256 candidates of a window batch (the fish of the 3x3 cell stencil, shifted
-// into the focal cell's frame) sit one per lane in registers (8 chunks of 32).  For each ACTIVE focal fish of the
-// cell (broadcast from shared memory):
-//   filter  - every lane tests its candidates with a cheap, conservative, sqrt-free predicate (inside the r=200
-//             disc and not clearly behind the 330 deg cone); survivors are compacted into a per-focal queue in
-//             shared memory with ballot/popc;
-//   process - the queue is consumed 32 entries at a time, one pair per lane, all lanes working for the SAME focal
-//             fish: exact classification (with the fp64 re-check of borderline pairs), zone counts by ballot, and the
-//             avoidance / alignment / attraction turn of the pair accumulated as fixed-point cos/sin in registers;
-//   reduce  - six warp REDUX adds fold the lanes' partial sums into the focal fish's 64-bit accumulators.
-// Lanes therefore stay full regardless of how many fish of the cell are active, and the expensive per-pair math only
-// runs on (almost only) interacting pairs.  Sums are integers, hence independent of candidate order: results are
-// bit-identical to the first design (neighbour_kernel) and across any re-sorting of the fish.
+// One warp owns one focal cell (persistent warps, cells handed out by an atomic counter).
+//   staging   the 3x3 stencil is ONE flattened run of candidates (9 cell ranges, prefix-summed once per cell); each
+//             lane copies candidates t = lane, lane+32, ... with a branch-free range lookup into the window (SoA x, y,
+//             cos, sin in the focal cell's frame).  The window is staged once per cell and reused by every focal
+//             group when the stencil fits it (<= 256 candidates).
+//   focal     the ACTIVE fish of the cell are compacted (ballot) into groups of up to 32, wherever they sit in the cell.
+//   filter    every lane tests its candidates (cached in registers, 8 chunks of 32) against one focal fish with a cheap,
+//             conservative, sqrt-free predicate (inside the r=200 disc and not clearly behind the 330 deg cone);
+//             survivors are compacted into a per-focal queue in shared memory with ballot/popc.
+//   process   the queue is consumed 32 entries at a time, one pair per lane, all lanes working for the SAME focal fish:
+//             exact classification (with the fp64 re-check of borderline pairs), zone counts and the avoidance /
+//             alignment / attraction turn of the pair as fixed-point cos/sin: the shared pair_math().
+//   reduce    eight warp REDUX adds fold the lanes' partial sums into the focal fish's 64-bit accumulators.
+// Lanes stay full regardless of how many fish of the cell are active, and the expensive per-pair math only runs on
+// (almost only) interacting pairs.  Sums are integers, hence independent of candidate order: results are bit-identical
+// to the first design (neighbour_kernel) and across any re-sorting or slab split of the fish.
+// (A half-warp-per-focal variant of process was measured 6 % slower at the benchmark density: queues of ~60 entries
+// fill two 32-wide rounds as well as four 16-wide ones, and the half-warp reductions cost twice the REDUX issue slots.)
 #pragma once
 #include "kernels.cuh"
 
@@ -21,27 +26,24 @@ namespace fishk {
 constexpr int V2_WARPS = 8;
 constexpr int V2_THREADS = V2_WARPS * 32;
 constexpr int V2_WIN = 256;           // candidates per window batch
-constexpr int V2_CH = V2_WIN / 32;    // register chunks per lane
 constexpr int V2_FMAX = 32;           // focal fish per group
 constexpr float V2_FAR = 1.0e18f;     // padding coordinate: fails the disc test
+constexpr float V2_KCONE = 0.93301270189f + 2.5e-4f;   // cos^2(165 deg) + margin
+constexpr float V2_R2HI = (CELL_F + 2.5e-4f) * (CELL_F + 2.5e-4f);
 
 struct V2WarpSmem {
     float wx[V2_WIN], wy[V2_WIN], wc[V2_WIN], ws[V2_WIN];  // window candidates in the focal cell's frame
-    uint32_t wcode[V2_WIN];                                // sorted index | stencil code << 28
     long long acc[V2_FMAX][6];                             // fixed-point cos/sin sums: avoid x,y, align x,y, attract x,y
-    int cnt[V2_FMAX][4];                                   // n15, n100, n200, front
+    int4 cnt[V2_FMAX];                                     // n15, n100, n200, front
     float4 frec[V2_FMAX];
     float fdir[V2_FMAX];
     int fidx[V2_FMAX];
     int fties[V2_FMAX];
+    int run_pre[12];                                       // exclusive prefix of the 9 stencil cells' counts (+ total)
+    int run_start[12];                                     // first sorted index of each stencil cell
     unsigned char queue[V2_WIN];
 };
-
 constexpr size_t V2_SMEM_BYTES = sizeof(V2WarpSmem) * V2_WARPS;
-
-// conservative cone test constant: cos^2(165 deg) + margin (see the band analysis in DESIGN.md)
-constexpr float V2_KCONE = 0.93301270189f + 2.5e-4f;
-constexpr float V2_R2HI = (CELL_F + 2.5e-4f) * (CELL_F + 2.5e-4f);
 
 template <bool STATS>
 __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const NeighArgs a) {
@@ -52,88 +54,115 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
     V2WarpSmem& S = reinterpret_cast<V2WarpSmem*>(v2_smem_raw)[warp];
 
     unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
-    // persistent warps: cells are handed out in order by an atomic counter (work per cell varies with occupancy)
-    while (true) {
-    int c = 0;
-    if (lane == 0) c = atomicAdd(a.work_counter, 1);
-    c = a.g.own_c0 + __shfl_sync(FULL, c, 0);
-    if (c >= a.g.own_c1) break;
-    const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
-    if (s0 == e0) continue;
-    int nb_s = 0, nb_e = 0;
-    if (lane < 9) {
-        const int cc = stencil_cell(a.g, c, lane);
-        nb_s = a.cell_start[cc];
-        nb_e = a.cell_start[cc + 1];
-    }
+    while (true) {  // persistent warps: cells are handed out in order by an atomic counter
+        int c = 0;
+        if (lane == 0) c = atomicAdd(a.work_counter, 1);
+        c = a.g.own_c0 + __shfl_sync(FULL, c, 0);
+        if (c >= a.g.own_c1) break;
+        const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
+        if (s0 == e0) continue;
 
-    for (int g0 = s0; g0 < e0; g0 += V2_FMAX) {
-        // ---- focal group: the active fish among 32 consecutive fish of the cell, compacted
-        const int i = g0 + lane;
-        const bool valid = i < e0;
-        float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
-        int4 c1 = make_int4(0, 0, 0, 0);
-        float dir_raw = 0.f;
-        if (valid) { me = a.rec[i]; c1 = a.cold1[i]; dir_raw = a.cold0[i].x; }
-        const bool active = valid && (a.active_lag_max < 0 || c1.x <= a.active_lag_max);
-        const unsigned amask = __ballot_sync(FULL, active);
-        const int nf = __popc(amask);
-        if (valid && !active) a.aux[i] = 0u;
-        if (nf == 0) continue;
-        __syncwarp();
-        if (active) {
-            const int slot = __popc(amask & lt_mask);
-            S.frec[slot] = me; S.fdir[slot] = dir_raw; S.fidx[slot] = i;
+        // ---- the stencil as one flattened run: per-cell ranges, exclusive prefix (lanes 0..8), total T
+        int nb_s = 0, nb_n = 0;
+        if (lane < 9) {
+            const int cc = stencil_cell(a.g, c, lane);
+            nb_s = a.cell_start[cc];
+            nb_n = a.cell_start[cc + 1] - nb_s;
         }
-        __syncwarp();
-        if (STATS) st_focal += (unsigned)nf;
-
-        // ---- window batches: the 9 stencil cells' fish are streamed through a WIN-entry window
-        int fill = 0, k = 0;
-        bool first_batch = true;
-        int ks = __shfl_sync(FULL, nb_s, 0), ke = __shfl_sync(FULL, nb_e, 0);
-        int b = ks;
-        bool more = true;
-        while (more) {
-            while (fill < V2_WIN && k < 9) {
-                if (b >= ke) {
-                    ++k;
-                    if (k < 9) { ks = __shfl_sync(FULL, nb_s, k); ke = __shfl_sync(FULL, nb_e, k); b = ks; }
-                    continue;
-                }
-                const float sx = (float)((k % 3) - 1) * CELL_F, sy = (float)((k / 3) - 1) * CELL_F;
-                const int m = min(ke - b, V2_WIN - fill);
-                for (int t = lane; t < m; t += 32) {
-                    const float4 r = __ldg(&a.rec[b + t]);
-                    S.wx[fill + t] = r.x + sx; S.wy[fill + t] = r.y + sy; S.wc[fill + t] = r.z; S.ws[fill + t] = r.w;
-                    S.wcode[fill + t] = (uint32_t)(b + t) | ((uint32_t)k << 28);
-                }
-                fill += m; b += m;
-            }
-            more = (k < 9);
-            if (fill > 0) {
-                // ======== one window batch of `fill` candidates ========
-                __syncwarp();
-                const int nch = (fill + 31) >> 5;
-                float cxr[V2_CH], cyr[V2_CH];
+        int pre = nb_n;
 #pragma unroll
-                for (int ch = 0; ch < V2_CH; ++ch) {
-                    const int j = ch * 32 + lane;
-                    const bool in = j < fill;
-                    cxr[ch] = in ? S.wx[j] : V2_FAR;
-                    cyr[ch] = in ? S.wy[j] : V2_FAR;
+        for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += t; }
+        const int T = __shfl_sync(FULL, pre, 8);
+        pre -= nb_n;
+        __syncwarp();
+        if (lane < 9) { S.run_pre[lane] = pre; S.run_start[lane] = nb_s; }
+        if (lane == 9) S.run_pre[9] = T;
+        __syncwarp();
+        const int nbatch = (T + V2_WIN - 1) / V2_WIN;
+        int staged = -1;  // batch currently in the window
+
+        auto stage = [&](int b) {
+            const int base = b * V2_WIN;
+            const int fill = min(T - base, V2_WIN);
+            const int padded = (fill + 31) & ~31;
+            const int p1 = S.run_pre[1], p2 = S.run_pre[2], p3 = S.run_pre[3], p4 = S.run_pre[4];
+            const int p5 = S.run_pre[5], p6 = S.run_pre[6], p7 = S.run_pre[7], p8 = S.run_pre[8];
+            for (int j = lane; j < padded; j += 32) {
+                float x = V2_FAR, y = V2_FAR, cs = 1.f, sn = 0.f;
+                if (j < fill) {
+                    const int t = base + j;
+                    const int k = (t >= p1) + (t >= p2) + (t >= p3) + (t >= p4) + (t >= p5) + (t >= p6) + (t >= p7) + (t >= p8);
+                    const float4 r = __ldg(&a.rec[S.run_start[k] + t - S.run_pre[k]]);
+                    const int ky = (k * 11) >> 5, kx = k - 3 * ky;  // k / 3, k % 3 for k < 9
+                    x = r.x + (float)(kx - 1) * CELL_F; y = r.y + (float)(ky - 1) * CELL_F; cs = r.z; sn = r.w;
+                }
+                S.wx[j] = x; S.wy[j] = y; S.wc[j] = cs; S.ws[j] = sn;
+            }
+            __syncwarp();
+            staged = b;
+            return fill;
+        };
+        // sorted index and stencil code of window slot j of batch b (rare paths only: fp64 re-check, tie draws)
+        auto locate = [&](int b, int j, int& src, int& k) {
+            const int t = b * V2_WIN + j;
+            k = 0;
+#pragma unroll
+            for (int m = 1; m < 9; ++m) k += (t >= S.run_pre[m]) ? 1 : 0;
+            src = S.run_start[k] + t - S.run_pre[k];
+        };
+
+        int pos = s0;
+        while (pos < e0) {
+            // ---- focal group: up to V2_FMAX active fish of the cell, compacted
+            int nf = 0;
+            __syncwarp();
+            while (pos < e0 && nf < V2_FMAX) {
+                const int i = pos + lane;
+                const bool valid = i < e0;
+                float4 me = make_float4(0.f, 0.f, 1.f, 0.f);
+                int lag = 0x7FFFFFFF;
+                if (valid) lag = a.cold1[i].x;
+                bool active = valid && (a.active_lag_max < 0 || lag <= a.active_lag_max);
+                unsigned amask = __ballot_sync(FULL, active);
+                int take = 32;  // fish of this 32-chunk consumed by this group
+                if (nf + __popc(amask) > V2_FMAX) {
+                    take = __fns(amask, 0, V2_FMAX - nf + 1);  // lane of the first active fish that no longer fits
+                    amask &= (1u << take) - 1u;
+                    active = active && lane < take;
+                }
+                if (valid && !active && lane < take) a.aux[i] = 0u;
+                if (active) {
+                    me = a.rec[i];
+                    const int slot = nf + __popc(amask & lt_mask);
+                    S.frec[slot] = me; S.fdir[slot] = a.cold0[i].x; S.fidx[slot] = i;
+                }
+                nf += __popc(amask);
+                pos += take;
+            }
+            __syncwarp();
+            if (nf == 0) continue;
+            if (STATS) st_focal += (unsigned)nf;
+
+            for (int b = 0; b < nbatch; ++b) {
+                const int fill = (staged == b) ? min(T - b * V2_WIN, V2_WIN) : stage(b);
+                const int nch = (fill + 31) >> 5;
+                float cxr[V2_WIN / 32], cyr[V2_WIN / 32];  // this lane's candidates (padding fails the disc test)
+#pragma unroll
+                for (int ch = 0; ch < V2_WIN / 32; ++ch) {
+                    const bool in = ch < nch;
+                    cxr[ch] = in ? S.wx[ch * 32 + lane] : V2_FAR;
+                    cyr[ch] = in ? S.wy[ch * 32 + lane] : V2_FAR;
                 }
                 for (int f = 0; f < nf; ++f) {
                     const float4 F = S.frec[f];  // broadcast
-                    const float fx = F.x, fy = F.y, fc = F.z, fs = F.w;
                     // ---- filter (all candidates, cheap, conservative)
                     int qn = 0;
 #pragma unroll
-                    for (int ch = 0; ch < V2_CH; ++ch) {
+                    for (int ch = 0; ch < V2_WIN / 32; ++ch) {
                         if (ch < nch) {
-                            const float dx = cxr[ch] - fx, dy = cyr[ch] - fy;
+                            const float dx = cxr[ch] - F.x, dy = cyr[ch] - F.y;
                             const float d2 = fmaf(dx, dx, dy * dy);
-                            const float dot = fmaf(fc, dx, fs * dy);
+                            const float dot = fmaf(F.z, dx, F.w * dy);
                             // inside the disc, and not clearly behind the cone: dot > -|cos165| d, written sqrt-free with the
                             // signed square; the +1 keeps every pair closer than 1 unit (its rounding band is wide)
                             const bool p = (d2 < V2_R2HI) && (fmaf(V2_KCONE, d2, dot * fabsf(dot)) > -1.0f);
@@ -154,14 +183,17 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                         const bool live = e < qn;
                         const int j = live ? (int)S.queue[e] : 0;
                         const bool unc = pair_math(
-                            live, fx, fy, fc, fs, fdir, exotic, S.wx[j], S.wy[j], S.wc[j], S.ws[j], a.seed, a.replicate, a.step_move,
+                            live, F.x, F.y, F.z, F.w, fdir, exotic, S.wx[j], S.wy[j], S.wc[j], S.ws[j], a.seed, a.replicate, a.step_move,
                             [&](float& rx, float& ry, int& kcode) {
-                                const uint32_t code = S.wcode[j];
-                                const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
-                                rx = raw.x; ry = raw.y; kcode = (int)(code >> 28);
+                                int src;
+                                locate(b, j, src, kcode);
+                                const float4 raw = __ldg(&a.rec[src]);
+                                rx = raw.x; ry = raw.y;
                             },
                             [&](uint32_t& my, uint32_t& nb) {
-                                nb = (uint32_t)a.cold1[S.wcode[j] & 0x0FFFFFFFu].w;
+                                int src, k;
+                                locate(b, j, src, k);
+                                nb = (uint32_t)a.cold1[src].w;
                                 my = (uint32_t)a.cold1[S.fidx[f]].w;
                             },
                             P);
@@ -172,49 +204,40 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                     const int r2 = __reduce_add_sync(FULL, P.ax1), r3 = __reduce_add_sync(FULL, P.ay1);
                     const int r4 = __reduce_add_sync(FULL, P.ax2), r5 = __reduce_add_sync(FULL, P.ay2);
                     const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
-                    const int c200 = cfar & 0xFFFF, cfr = cfar >> 16, c100 = cnear & 0xFFFF, c15 = cnear >> 16;
                     const int tsum = __any_sync(FULL, P.ties != 0) ? __reduce_add_sync(FULL, P.ties) : 0;
-                    if (STATS) st_inter += (unsigned)c200;
+                    if (STATS) st_inter += (unsigned)(cfar & 0xFFFF);
                     if (lane == 0) {
-                        if (first_batch) {
+                        const int4 cc = make_int4(cnear >> 16, cnear & 0xFFFF, cfar & 0xFFFF, cfar >> 16);
+                        if (b == 0) {
                             S.acc[f][0] = r0; S.acc[f][1] = r1; S.acc[f][2] = r2; S.acc[f][3] = r3; S.acc[f][4] = r4; S.acc[f][5] = r5;
-                            *reinterpret_cast<int4*>(&S.cnt[f][0]) = make_int4(c15, c100, c200, cfr);
+                            S.cnt[f] = cc;
                             S.fties[f] = tsum;
                         } else {
                             S.acc[f][0] += r0; S.acc[f][1] += r1; S.acc[f][2] += r2; S.acc[f][3] += r3; S.acc[f][4] += r4; S.acc[f][5] += r5;
-                            int4 cc = *reinterpret_cast<int4*>(&S.cnt[f][0]);
-                            cc.x += c15; cc.y += c100; cc.z += c200; cc.w += cfr;
-                            *reinterpret_cast<int4*>(&S.cnt[f][0]) = cc;
+                            int4 o = S.cnt[f];
+                            o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+                            S.cnt[f] = o;
                             S.fties[f] += tsum;
                         }
                     }
                     __syncwarp();
                 }
             }
-            if (fill > 0) first_batch = false;
-            fill = 0;
+            // ---- epilogue, one focal fish per lane
+            __syncwarp();
+            if (lane < nf) {
+                const int idx = S.fidx[lane];
+                const int4 k1 = a.cold1[idx];
+                const int4 cc = S.cnt[lane];
+                const float4 F = S.frec[lane];
+                finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], S.fties[lane]);
+            }
+            __syncwarp();
         }
-
-        // ---- epilogue, one focal fish per lane: social()'s selection (fish_mod.cpp:355-376), averageturn (:379-408),
-        //      random walk (:372-374) and sample()'s feeding decision (:543-547)
-        __syncwarp();
-        if (lane < nf) {
-            const int f = lane;
-            const int idx = S.fidx[f];
-            const int4 k1 = a.cold1[idx];
-            const int n15 = S.cnt[f][0], n100 = S.cnt[f][1], n200 = S.cnt[f][2], nfr = S.cnt[f][3];
-            const float4 F = S.frec[f];
-            finish_focal(a, idx, k1, F.x, F.y, n15, n100, n200, nfr, &S.acc[f][0], S.fties[f]);
-        }
-        __syncwarp();
     }
-    }  // persistent loop
-    if (STATS && a.stats) {
-        // st_* are warp-uniform except st_rechk (uniform too: from ballots)
-        if (lane == 0) {
-            atomicAdd(&a.stats[0], st_focal); atomicAdd(&a.stats[1], st_cand);
-            atomicAdd(&a.stats[2], st_inter); atomicAdd(&a.stats[3], st_rechk);
-        }
+    if (STATS && a.stats && lane == 0) {
+        atomicAdd(&a.stats[0], st_focal); atomicAdd(&a.stats[1], st_cand);
+        atomicAdd(&a.stats[2], st_inter); atomicAdd(&a.stats[3], st_rechk);
     }
 }
 
