@@ -33,6 +33,11 @@ class PassStats(C.Structure):
                 ("rechecked", C.c_uint64)]
 
 
+class SlabEndpoint(C.Structure):
+    _fields_ = [("ipc_handle", C.c_ubyte * 64), ("raw_pointer", C.c_uint64), ("bytes", C.c_int64),
+                ("pid", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("pad", C.c_int32)]
+
+
 # every symbol include/fishabm.h declares (tests check the library exports each of them)
 SYMBOLS = [
     "fishabm_params_default", "fishabm_create", "fishabm_destroy", "fishabm_last_error", "fishabm_set_state",
@@ -43,7 +48,8 @@ SYMBOLS = [
     "fishabm_last_pass_stats", "fishabm_launch_count", "fishabm_enable_stats", "fishabm_averageturn",
     "fishabm_correctangle", "fishabm_correct_coords",
     "fishabm_slab_get_info", "fishabm_slab_unique_id", "fishabm_slab_connect", "fishabm_slab_begin_step",
-    "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy",
+    "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy", "fishabm_slab_get_endpoint",
+    "fishabm_slab_attach", "fishabm_step_enqueue", "fishabm_wait",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -103,5 +109,9 @@ def load():
     L.fishabm_slab_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64)]
     L.fishabm_slab_end_step.argtypes = [vp]
     L.fishabm_slab_copy.argtypes = [vp, vp, C.c_int64]
+    L.fishabm_slab_get_endpoint.argtypes = [vp, C.POINTER(SlabEndpoint)]
+    L.fishabm_slab_attach.argtypes = [vp, C.POINTER(SlabEndpoint), C.POINTER(SlabEndpoint)]
+    L.fishabm_step_enqueue.argtypes = [vp, i32]
+    L.fishabm_wait.argtypes = [vp]
     _lib = L
     return L

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -55,6 +56,15 @@ struct fishabm_ctx {
     size_t msg_bytes = 0;
     unsigned char *out_left = nullptr, *out_right = nullptr, *in_left = nullptr, *in_right = nullptr;
     void* comm = nullptr;  // ncclComm_t once connected
+    // peer-memory transport: my inbox [2 sides][2 slots] + flags; the neighbours' inboxes once attached
+    unsigned char* inbox = nullptr;
+    size_t msg_stride = 0, inbox_bytes = 0;
+    unsigned char *peer_left = nullptr, *peer_right = nullptr;
+    void* ipc_opened[2] = {nullptr, nullptr};
+    bool p2p = false;
+    int seq = 0;                 // exchanges completed (the same on every rank)
+    SlabHeader* ctr = nullptr;   // [2] local slot counters while packing into remote inboxes
+    long long timeout_ns = 10000000000LL;
     bool step_open = false;  // between fishabm_slab_begin_step and fishabm_slab_end_step
     int* n_unsorted = nullptr;
     int* err = nullptr;
@@ -154,7 +164,11 @@ NcclApi& nccl() {
         if (r_ != 0) return fail(ctx, FISHABM_E_COMM, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r_) : "nccl error"); \
     } while (0)
 
-SlabMsg msg(const fishabm_ctx* c, unsigned char* base) { return SlabMsg{base, c->cap_m, c->cap_g}; }
+SlabMsg msg(const fishabm_ctx* c, unsigned char* base, SlabHeader* counters = nullptr) { return SlabMsg{base, c->cap_m, c->cap_g, counters}; }
+// inbox layout: side 0 = messages from my left neighbour, side 1 = from my right; two slots per side (alternating
+// exchanges: a neighbour may already be packing exchange s+1 while exchange s is still being ingested here)
+size_t inbox_msg_off(const fishabm_ctx* c, int side, int slot) { return (size_t)(side * 2 + slot) * c->msg_stride; }
+size_t inbox_flag_off(const fishabm_ctx* c, int side, int slot) { return 4 * c->msg_stride + (size_t)(side * 2 + slot) * 128; }
 
 // ---- the counting sort: counts (already accumulated in cell_count) -> cell_start; scatter cur -> other
 int rebuild(fishabm_ctx* ctx) {
@@ -228,8 +242,16 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.slab = ctx->slab ? 1 : 0;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) {
-        CK(cudaMemsetAsync(ctx->out_left, 0, sizeof(SlabHeader), ctx->stream));
-        CK(cudaMemsetAsync(ctx->out_right, 0, sizeof(SlabHeader), ctx->stream));
+        if (ctx->p2p) {
+            // pack straight into the neighbours' inboxes: what leaves through my LEFT edge arrives from the RIGHT there
+            const int slot = (ctx->seq + 1) & 1;
+            u.out_left = msg(ctx, ctx->peer_left + inbox_msg_off(ctx, 1, slot), ctx->ctr + 0);
+            u.out_right = msg(ctx, ctx->peer_right + inbox_msg_off(ctx, 0, slot), ctx->ctr + 1);
+            CK(cudaMemsetAsync(ctx->ctr, 0, 2 * sizeof(SlabHeader), ctx->stream));
+        } else {
+            CK(cudaMemsetAsync(ctx->out_left, 0, sizeof(SlabHeader), ctx->stream));
+            CK(cudaMemsetAsync(ctx->out_right, 0, sizeof(SlabHeader), ctx->stream));
+        }
     }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
@@ -258,7 +280,23 @@ int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_righ
 // the exchange the library drives itself: a lone slab is its own neighbour on both sides; several slabs use NCCL
 int exchange(fishabm_ctx* ctx, unsigned char** in_left, unsigned char** in_right) {
     if (ctx->p.nranks == 1) { *in_left = ctx->out_right; *in_right = ctx->out_left; return 0; }
-    if (!ctx->comm) return fail(ctx, FISHABM_E_STATE, "slab context is not connected: call fishabm_slab_connect, or drive the exchange with fishabm_slab_begin_step / end_step");
+    if (ctx->p2p) {
+        const int s = ++ctx->seq, slot = s & 1;
+        SlabPublishArgs pa{ctx->ctr + 0, ctx->ctr + 1,
+                           reinterpret_cast<SlabHeader*>(ctx->peer_left + inbox_msg_off(ctx, 1, slot)),
+                           reinterpret_cast<SlabHeader*>(ctx->peer_right + inbox_msg_off(ctx, 0, slot)),
+                           reinterpret_cast<int*>(ctx->peer_left + inbox_flag_off(ctx, 1, slot)),
+                           reinterpret_cast<int*>(ctx->peer_right + inbox_flag_off(ctx, 0, slot)), s};
+        slab_publish_kernel<<<1, 32, 0, ctx->stream>>>(pa);
+        slab_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<int*>(ctx->inbox + inbox_flag_off(ctx, 0, slot)),
+                                                    reinterpret_cast<int*>(ctx->inbox + inbox_flag_off(ctx, 1, slot)), s, ctx->timeout_ns, ctx->err);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        *in_left = ctx->inbox + inbox_msg_off(ctx, 0, slot);
+        *in_right = ctx->inbox + inbox_msg_off(ctx, 1, slot);
+        return 0;
+    }
+    if (!ctx->comm) return fail(ctx, FISHABM_E_STATE, "slab context is not connected: call fishabm_slab_attach or fishabm_slab_connect, or drive the exchange with fishabm_slab_begin_step / end_step");
     NcclApi& N = nccl();
     NK(N.GroupStart());
     NK(N.Send(ctx->out_left, ctx->msg_bytes, NCCL_UINT8, ctx->left, ctx->comm, ctx->stream));
@@ -290,6 +328,7 @@ int check_device_errors(fishabm_ctx* ctx) {
     CK(cudaMemcpyAsync(&e, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (e & ERR_SLAB_OVERFLOW) return fail(ctx, FISHABM_E_NOMEM, "slab capacity exceeded (capacity %d, halo_capacity %d, migrant_capacity %d): raise fishabm_params.capacity / halo_capacity / migrant_capacity", ctx->cap, ctx->cap_g, ctx->cap_m);
+    if (e & ERR_SLAB_TIMEOUT) return fail(ctx, FISHABM_E_COMM, "a neighbour slab's message did not arrive within %.1f s (peer-memory transport)", ctx->timeout_ns * 1e-9);
     if (e & ERR_STEP_TOO_LONG) return fail(ctx, FISHABM_E_ARG, "a fish moved more than 200 units in one step: not supported with slabs");
     return 0;
 }
@@ -511,6 +550,11 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (c->slab) {
         A(dalloc(&c->out_left, c->msg_bytes)); A(dalloc(&c->out_right, c->msg_bytes));
         A(dalloc(&c->in_left, c->msg_bytes)); A(dalloc(&c->in_right, c->msg_bytes));
+        c->msg_stride = (c->msg_bytes + 255) & ~(size_t)255;
+        c->inbox_bytes = 4 * c->msg_stride + 8 * 128;
+        A(dalloc(&c->inbox, c->inbox_bytes)); A(dalloc(&c->ctr, 2));
+        if (ok) A(cudaMemset(c->inbox, 0, c->inbox_bytes));
+        if (const char* t = getenv("FISHABM_SLAB_TIMEOUT_MS")) c->timeout_ns = atoll(t) * 1000000LL;
     }
     if (ok) {
         A(cudaMemset(c->cell_count, 0, ((size_t)c->ncell + 1) * sizeof(int)));
@@ -554,6 +598,8 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
+    for (void* q : c->ipc_opened) if (q) cudaIpcCloseMemHandle(q);
+    cudaFree(c->inbox); cudaFree(c->ctr);
     for (int k = 0; k < 2; ++k) { cudaFree(c->buf[k].rec); cudaFree(c->buf[k].cold0); cudaFree(c->buf[k].cold1); cudaFree(c->buf[k].cell); }
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
@@ -1080,6 +1126,71 @@ int fishabm_slab_end_step(fishabm_ctx* ctx) {
     ctx->step += 1;
     CK(cudaStreamSynchronize(ctx->stream));
     return check_device_errors(ctx);
+}
+
+int fishabm_slab_get_endpoint(fishabm_ctx* ctx, fishabm_slab_endpoint* out) {
+    if (!ctx || !out) return FISHABM_E_ARG;
+    if (!ctx->slab || !ctx->inbox) return fail(ctx, FISHABM_E_STATE, "not a slab context");
+    CK(cudaSetDevice(ctx->p.device));
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) <= sizeof(out->ipc_handle), "ipc handle size");
+    CK(cudaIpcGetMemHandle(&h, ctx->inbox));
+    memcpy(out->ipc_handle, &h, sizeof h);
+    out->raw_pointer = (uint64_t)(uintptr_t)ctx->inbox;
+    out->bytes = (int64_t)ctx->inbox_bytes;
+    out->pid = (int32_t)getpid(); out->device = ctx->p.device; out->rank = ctx->p.rank;
+    return 0;
+}
+
+int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, const fishabm_slab_endpoint* right) {
+    if (!ctx || !left || !right) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: null argument");
+    if (!ctx->slab || ctx->p.nranks < 2) return fail(ctx, FISHABM_E_STATE, "fishabm_slab_attach: the context is not one of several slabs");
+    if (ctx->p2p) return fail(ctx, FISHABM_E_STATE, "fishabm_slab_attach: already attached");
+    if (left->rank != ctx->left || right->rank != ctx->right) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: endpoints of ranks %d / %d given, neighbours are %d / %d", left->rank, right->rank, ctx->left, ctx->right);
+    if (left->bytes != (int64_t)ctx->inbox_bytes || right->bytes != (int64_t)ctx->inbox_bytes) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: the neighbours' message capacities differ from mine");
+    CK(cudaSetDevice(ctx->p.device));
+    const fishabm_slab_endpoint* eps[2] = {left, right};
+    unsigned char* ptr[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && left->pid == right->pid && left->raw_pointer == right->raw_pointer) { ptr[1] = ptr[0]; break; }  // two ranks: one peer
+        const fishabm_slab_endpoint* e = eps[k];
+        if (e->pid == (int32_t)getpid()) {
+            if (e->device != ctx->p.device) {
+                cudaError_t r = cudaDeviceEnablePeerAccess(e->device, 0);
+                if (r == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (r != cudaSuccess) return fail(ctx, FISHABM_E_COMM, "no peer access from device %d to %d: %s", ctx->p.device, e->device, cudaGetErrorString(r));
+            }
+            ptr[k] = reinterpret_cast<unsigned char*>((uintptr_t)e->raw_pointer);
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, e->ipc_handle, sizeof h);
+            void* q = nullptr;
+            cudaError_t r = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+            if (r != cudaSuccess) return fail(ctx, FISHABM_E_COMM, "cudaIpcOpenMemHandle (rank %d's inbox): %s", e->rank, cudaGetErrorString(r));
+            ctx->ipc_opened[k] = q;
+            ptr[k] = static_cast<unsigned char*>(q);
+        }
+    }
+    ctx->peer_left = ptr[0]; ctx->peer_right = ptr[1];
+    ctx->p2p = true;
+    return 0;
+}
+
+int fishabm_step_enqueue(fishabm_ctx* ctx, int32_t nsteps) {
+    int rc = need_state(ctx);
+    if (rc) return rc;
+    if (nsteps < 1) return fail(ctx, FISHABM_E_ARG, "nsteps must be >= 1");
+    CK(cudaSetDevice(ctx->p.device));
+    if (ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_step_enqueue is for single schools / slabs");
+    if ((rc = begin_timed(ctx))) return rc;
+    return step_untimed(ctx, nsteps);
+}
+
+int fishabm_wait(fishabm_ctx* ctx) {
+    if (!ctx) return FISHABM_E_ARG;
+    CK(cudaSetDevice(ctx->p.device));
+    return end_timed(ctx);
 }
 
 int fishabm_slab_copy(void* dst, const void* src, int64_t bytes) {

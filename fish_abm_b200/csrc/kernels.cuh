@@ -501,9 +501,11 @@ struct MigRec { float4 rec; float4 cold0; int4 cold1; int cy; int pad[3]; };
 struct GhostRec { float4 rec; int id; int cy; int pad[2]; };
 
 struct SlabMsg {  // view of one message buffer
-    unsigned char* base;
+    unsigned char* base;   // header + payload (in peer-memory transport: the NEIGHBOUR's inbox, written over NVLink)
     int cap_m, cap_g;
-    __host__ __device__ SlabHeader* hdr() const { return reinterpret_cast<SlabHeader*>(base); }
+    SlabHeader* counters;  // where slots are claimed while packing: the header itself, or (peer-memory transport) a local
+                           // copy that slab_publish_kernel writes into the remote header once the payload is complete
+    __host__ __device__ SlabHeader* hdr() const { return counters ? counters : reinterpret_cast<SlabHeader*>(base); }
     __host__ __device__ MigRec* mig() const { return reinterpret_cast<MigRec*>(base + sizeof(SlabHeader)); }
     __host__ __device__ GhostRec* ghost() const { return reinterpret_cast<GhostRec*>(base + sizeof(SlabHeader) + (size_t)cap_m * sizeof(MigRec)); }
     __host__ __device__ static size_t bytes(int cap_m, int cap_g) { return sizeof(SlabHeader) + (size_t)cap_m * sizeof(MigRec) + (size_t)cap_g * sizeof(GhostRec); }
@@ -562,6 +564,38 @@ struct UpdateArgs {
 
 constexpr int ERR_SLAB_OVERFLOW = 1;   // a slab message or the fish arrays overflowed their capacity
 constexpr int ERR_STEP_TOO_LONG = 2;   // a fish moved further than one neighbour cell in one step (slab mode)
+constexpr int ERR_SLAB_TIMEOUT = 4;    // a neighbour's message did not arrive (peer-memory transport)
+
+// ---- peer-memory transport: the update kernel has stored this step's payload directly into the two neighbours'
+// inboxes (NVLink peer stores).  publish: complete each remote message with its header, then raise its flag (release,
+// system scope).  wait: spin (bounded) until both of MY inbox slots carry this step's sequence number (acquire).
+struct SlabPublishArgs {
+    const SlabHeader* counters_left; const SlabHeader* counters_right;
+    SlabHeader* remote_left_hdr; SlabHeader* remote_right_hdr;
+    int* remote_left_flag; int* remote_right_flag;
+    int seq;
+};
+__global__ void slab_publish_kernel(const SlabPublishArgs a) {
+    if (threadIdx.x >= 2) return;
+    const SlabHeader h = threadIdx.x == 0 ? *a.counters_left : *a.counters_right;
+    SlabHeader* rh = threadIdx.x == 0 ? a.remote_left_hdr : a.remote_right_hdr;
+    int* rf = threadIdx.x == 0 ? a.remote_left_flag : a.remote_right_flag;
+    *rh = h;
+    __threadfence_system();  // payload (previous kernel) and header are ordered before the flag, system-wide
+    *reinterpret_cast<volatile int*>(rf) = a.seq;
+}
+__global__ void slab_wait_kernel(const int* flag_left, const int* flag_right, int seq, long long timeout_ns, int* err) {
+    if (threadIdx.x >= 2) return;
+    const volatile int* f = threadIdx.x == 0 ? flag_left : flag_right;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (*f - seq < 0) {  // wrap-safe "flag < seq"
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if ((long long)(t - t0) > timeout_ns) { atomicOr(err, ERR_SLAB_TIMEOUT); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
 
 __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

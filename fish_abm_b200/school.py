@@ -228,6 +228,23 @@ class School:
         buf = (C.c_char * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
         self._ck(self.L.fishabm_slab_connect(self.ctx, C.cast(buf, C.c_void_p), _lib.UNIQUE_ID_BYTES))
 
+    def slab_endpoint(self) -> bytes:
+        """this slab's inbox (peer-memory transport) as opaque bytes to hand to its neighbours"""
+        e = _lib.SlabEndpoint()
+        self._ck(self.L.fishabm_slab_get_endpoint(self.ctx, C.byref(e)))
+        return bytes(e)
+
+    def slab_attach(self, left: bytes, right: bytes):
+        """attach to the two neighbours' inboxes: from now on move() packs straight into them over NVLink"""
+        l, r = _lib.SlabEndpoint.from_buffer_copy(left), _lib.SlabEndpoint.from_buffer_copy(right)
+        self._ck(self.L.fishabm_slab_attach(self.ctx, C.byref(l), C.byref(r)))
+
+    def step_enqueue(self, nsteps: int = 1):
+        self._ck(self.L.fishabm_step_enqueue(self.ctx, int(nsteps)))
+
+    def wait(self):
+        self._ck(self.L.fishabm_wait(self.ctx))
+
     def slab_begin_step(self):
         self._ck(self.L.fishabm_slab_begin_step(self.ctx))
 

@@ -85,15 +85,36 @@ def broadcast_unique_id(dist, rank: int, device=None) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-class DistributedSchool(School):
-    """This rank's slab.  `dist` is an initialised torch.distributed module/group used only for the bootstrap."""
+def gather_endpoints(dist, endpoint: bytes, device=None):
+    """every rank's inbox endpoint, in rank order"""
+    import torch
+    n = dist.get_world_size()
+    mine = torch.frombuffer(bytearray(endpoint), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.zeros_like(mine) for _ in range(n)]
+    dist.all_gather(parts, mine)
+    return [bytes(p.cpu().numpy().tobytes()) for p in parts]
 
-    def __init__(self, dist, rank: int, nranks: int, device: int, **kw):
+
+class DistributedSchool(School):
+    """This rank's slab.  `dist` is an initialised torch.distributed module/group used only for the bootstrap.
+    transport: "p2p" = peer-memory inboxes over NVLink (default), "nccl" = ncclSend/ncclRecv inside the library
+    (FISHABM_SLAB_TRANSPORT overrides)."""
+
+    def __init__(self, dist, rank: int, nranks: int, device: int, transport: str | None = None, **kw):
         super().__init__(rank=rank, nranks=nranks, device=device, **kw)
+        self.transport = transport or os.environ.get("FISHABM_SLAB_TRANSPORT", "p2p")
         if nranks > 1:
             import torch
             dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else None
-            self.slab_connect(broadcast_unique_id(dist, rank, dev))
+            if self.transport == "nccl":
+                self.slab_connect(broadcast_unique_id(dist, rank, dev))
+            else:
+                eps = gather_endpoints(dist, self.slab_endpoint(), dev)
+                left, right = ring(rank, nranks)
+                self.slab_attach(eps[left], eps[right])
+                dist.barrier()  # nobody starts storing into an inbox before everyone has attached
 
 
 # ---- several slabs in one process -----------------------------------------------------------------------------------------
@@ -101,11 +122,20 @@ class LocalSlabs:
     """nslabs contexts in this process; step() drives the exchange through the caller-driven hooks
     (fishabm_slab_begin_step / fishabm_slab_buffers / fishabm_slab_end_step)."""
 
-    def __init__(self, nslabs: int, devices=None, **kw):
+    def __init__(self, nslabs: int, devices=None, transport: str = "hooks", **kw):
+        """transport "hooks": this class copies the messages (caller-driven exchange); "p2p": the slabs are attached
+        to each other's inboxes and exchange by themselves (peer-memory transport, here inside one process)"""
         self.k = nslabs
+        self.transport = transport
         devices = devices or [0] * nslabs
         self.S = [School(rank=r, nranks=nslabs, device=devices[r], force_slab=True, **kw) for r in range(nslabs)]
         self.n, self.w, self.h = self.S[0].n, self.S[0].w, self.S[0].h
+        if transport == "p2p":
+            assert nslabs > 1
+            eps = [s.slab_endpoint() for s in self.S]
+            for r, s in enumerate(self.S):
+                left, right = ring(r, nslabs)
+                s.slab_attach(eps[left], eps[right])
 
     def close(self):
         for s in self.S:
@@ -131,6 +161,18 @@ class LocalSlabs:
 
     def step(self, nsteps: int = 1):
         L = self.S[0].L
+        if self.transport == "p2p":
+            # every slab waits (on the device) for its neighbours' messages: enqueue all of them before waiting for
+            # any, in chunks short enough for the launch queues
+            done = 0
+            while done < nsteps:
+                k = min(16, nsteps - done)
+                for s in self.S:
+                    s.step_enqueue(k)
+                for s in self.S:
+                    s.wait()
+                done += k
+            return
         for _ in range(nsteps):
             for s in self.S:
                 s.slab_begin_step()

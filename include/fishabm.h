@@ -197,6 +197,25 @@ int fishabm_slab_buffers(fishabm_ctx* ctx, void** out_left, void** out_right, vo
 int fishabm_slab_end_step(fishabm_ctx* ctx);
 /* device-to-device copy helper for the caller-driven exchange (cudaMemcpy, synchronous) */
 int fishabm_slab_copy(void* dst_device, const void* src_device, int64_t bytes);
+/* Peer-memory transport (preferred on NVLink / NVSwitch boxes): every slab owns an INBOX (two sides x two slots of one
+ * message each, plus arrival flags) in its GPU's memory.  Once a slab is attached to its two neighbours' inboxes, the
+ * update kernel stores each migrant / ghost record directly into the neighbour's inbox over NVLink while it packs,
+ * a one-warp kernel completes the header and raises the arrival flag, and a one-warp kernel on the receiving side
+ * waits for both flags: no copy kernel, no NCCL launch, no host involvement.  fishabm_slab_endpoint describes the
+ * inbox (CUDA IPC handle for other processes, raw pointer for contexts of the same process); the caller carries the
+ * endpoints between ranks.  Attach replaces the NCCL connection; it is collective in the same sense. */
+typedef struct fishabm_slab_endpoint {
+    unsigned char ipc_handle[64];  /* cudaIpcMemHandle_t of the inbox allocation */
+    uint64_t raw_pointer;          /* the same allocation's device pointer, valid inside the owning process */
+    int64_t bytes;                 /* size of the inbox allocation */
+    int32_t pid, device, rank, pad;
+} fishabm_slab_endpoint;
+int fishabm_slab_get_endpoint(fishabm_ctx* ctx, fishabm_slab_endpoint* out);
+int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, const fishabm_slab_endpoint* right);
+/* fishabm_step without the final host synchronisation, and the matching wait (several contexts of one process that
+ * are each other's neighbours must all be enqueued before any of them can finish) */
+int fishabm_step_enqueue(fishabm_ctx* ctx, int32_t nsteps);
+int fishabm_wait(fishabm_ctx* ctx);
 
 /* ---- host-side scalar helpers with the reference's semantics (not on the hot path) ---------------------- */
 double fishabm_averageturn(const double* v, int32_t n, int32_t comb_weight); /* fish_mod.cpp:379-408 */

@@ -71,6 +71,39 @@ def test_local_slabs_equal_whole_school(q100, nslabs):
         assert P.sum_array() == int(qa.sum())
 
 
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+def test_peer_memory_transport_in_one_process(q100, nslabs, monkeypatch):
+    """the slabs pack straight into each other's inboxes and synchronise with device-side flags (here all on one GPU)"""
+    monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "4000")
+    n, w, steps = 30_000, 7 * 200 * 2, 21
+    d = synth.uniform_state(n, w, w, seed=43, speed=12.0)
+    q = synth.tile_quality(q100, w, w)
+    zc0, g, qa, zc1, turn = whole_school(n, w, d, q, 78, steps)
+    with LocalSlabs(nslabs, transport="p2p", n=n, w=w, h=w, seed=78) as P:
+        P.set_state(**d)
+        P.set_quality(q)
+        P.step(steps)
+        assert_same(P.get_state(), g)
+        assert np.array_equal(P.get_quality(), qa)
+        assert np.array_equal(P.zone_counts(), zc1)
+        assert np.array_equal(P.social_turn(), turn)
+
+
+def test_peer_memory_timeout_is_reported_not_hung(q100, monkeypatch):
+    """a neighbour that never steps: the wait kernel gives up after the timeout and the call reports it"""
+    from fish_abm_b200 import FishAbmError
+    monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "300")
+    n, w = 5_000, 2000
+    d = synth.uniform_state(n, w, w, seed=48)
+    with LocalSlabs(2, transport="p2p", n=n, w=w, h=w, seed=3) as P:
+        P.set_state(**d)
+        P.set_quality(q100)
+        P.S[0].step_enqueue(1)
+        with pytest.raises(FishAbmError) as e:
+            P.S[0].wait()
+        assert e.value.code == -5 and "did not arrive" in str(e.value)
+
+
 def test_one_column_slabs_are_rejected(q100):
     """a slab needs two owned columns (a migrant into a one-column slab would also be a ghost for the slab beyond)"""
     from fish_abm_b200 import FishAbmError
@@ -114,14 +147,18 @@ def test_unconnected_multi_rank_step_fails_loudly(q100):
         assert e.value.code == -3
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_nccl_slabs_equal_whole_school(q100, tmp_path, nranks):
-    """one process per GPU, exchange inside the library over NCCL; needs that many GPUs on the box"""
+def test_multi_gpu_slabs_equal_whole_school(q100, tmp_path, nranks, transport, monkeypatch):
+    """one process per GPU; the exchange runs inside the library: peer-memory inboxes over NVLink (CUDA IPC), or NCCL
+    send/recv.  Needs that many GPUs on the box."""
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
+    monkeypatch.setenv("FISHABM_SLAB_TRANSPORT", transport)
+    monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "20000")
     out = tmp_path / "res.npz"
-    port = 29650 + nranks
+    port = 29650 + nranks + (10 if transport == "nccl" else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
