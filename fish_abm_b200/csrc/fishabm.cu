@@ -227,6 +227,22 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     return 0;
 }
 
+// the two messages of the coming exchange, emptied: local buffers (NCCL / caller-driven / lone slab) or, with the
+// peer-memory transport, the neighbours' inboxes themselves (what leaves through my LEFT edge arrives from the RIGHT there)
+int open_out_messages(fishabm_ctx* ctx, SlabMsg* out_left, SlabMsg* out_right) {
+    if (ctx->p2p) {
+        const int slot = (ctx->seq + 1) & 1;
+        *out_left = msg(ctx, ctx->peer_left + inbox_msg_off(ctx, 1, slot), ctx->ctr + 0);
+        *out_right = msg(ctx, ctx->peer_right + inbox_msg_off(ctx, 0, slot), ctx->ctr + 1);
+        CK(cudaMemsetAsync(ctx->ctr, 0, 2 * sizeof(SlabHeader), ctx->stream));
+    } else {
+        *out_left = msg(ctx, ctx->out_left); *out_right = msg(ctx, ctx->out_right);
+        CK(cudaMemsetAsync(ctx->out_left, 0, sizeof(SlabHeader), ctx->stream));
+        CK(cudaMemsetAsync(ctx->out_right, 0, sizeof(SlabHeader), ctx->stream));
+    }
+    return 0;
+}
+
 // K5 (+ deferred food-grid writes); a move also packs the slab messages
 int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
     const Buffers& b = ctx->buf[ctx->cur];
@@ -241,18 +257,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = ctx->p.replicate0; u.speed_norm = ctx->speed_norm;
     u.slab = ctx->slab ? 1 : 0;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
-    if (ctx->slab && do_move) {
-        if (ctx->p2p) {
-            // pack straight into the neighbours' inboxes: what leaves through my LEFT edge arrives from the RIGHT there
-            const int slot = (ctx->seq + 1) & 1;
-            u.out_left = msg(ctx, ctx->peer_left + inbox_msg_off(ctx, 1, slot), ctx->ctr + 0);
-            u.out_right = msg(ctx, ctx->peer_right + inbox_msg_off(ctx, 0, slot), ctx->ctr + 1);
-            CK(cudaMemsetAsync(ctx->ctr, 0, 2 * sizeof(SlabHeader), ctx->stream));
-        } else {
-            CK(cudaMemsetAsync(ctx->out_left, 0, sizeof(SlabHeader), ctx->stream));
-            CK(cudaMemsetAsync(ctx->out_right, 0, sizeof(SlabHeader), ctx->stream));
-        }
-    }
+    if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
     if (do_sample) {
@@ -324,9 +329,17 @@ int begin_timed(fishabm_ctx* ctx) {
 }
 int check_device_errors(fishabm_ctx* ctx) {
     if (!ctx->slab) return 0;
-    int e = 0;
+    int e = 0, bad = 0;
     CK(cudaMemcpyAsync(&e, ctx->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&bad, ctx->bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+        ctx->have_state = false;
+        CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), ctx->stream));
+        if (bad & 1) return fail(ctx, FISHABM_E_ARG, "set_state: coordinates must be finite and inside [0,w] x [0,h]");
+        if (bad & 4) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: a fish lies outside this slab's columns [%d, %d)", ctx->col0, ctx->col0 + ctx->own);
+        return fail(ctx, FISHABM_E_NOMEM, "set_state: this slab holds more than its capacity of %d entries: raise fishabm_params.capacity", ctx->cap);
+    }
     if (e & ERR_SLAB_OVERFLOW) return fail(ctx, FISHABM_E_NOMEM, "slab capacity exceeded (capacity %d, halo_capacity %d, migrant_capacity %d): raise fishabm_params.capacity / halo_capacity / migrant_capacity", ctx->cap, ctx->cap_g, ctx->cap_m);
     if (e & ERR_SLAB_TIMEOUT) return fail(ctx, FISHABM_E_COMM, "a neighbour slab's message did not arrive within %.1f s (peer-memory transport)", ctx->timeout_ns * 1e-9);
     if (e & ERR_STEP_TOO_LONG) return fail(ctx, FISHABM_E_ARG, "a fish moved more than 200 units in one step: not supported with slabs");
@@ -657,7 +670,7 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     CK(cudaMemcpyAsync(ctx->n_unsorted, &ctx->h_n, sizeof(int), cudaMemcpyHostToDevice, s));
     const Buffers& b = ctx->buf[ctx->cur];
     IngestArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake,
-                 b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted,
+                 b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted, nullptr,
                  ctx->n, ctx->cap, ctx->g, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
     ingest_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
@@ -669,6 +682,94 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     if (bad & 1) { ctx->have_state = false; return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: coordinates must be finite and inside [0,w] x [0,h]"); }
     if (bad & 2) { ctx->have_state = false; return fail(ctx, FISHABM_E_NOMEM, "fishabm_set_state: this slab holds more than its capacity of %d entries: raise fishabm_params.capacity", ctx->cap); }
     ctx->have_state = true;
+    return 0;
+}
+
+int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids, const double* coords, const double* dir,
+                            const double* speed, const double* speed_factor, const int32_t* lag, const int32_t* sample_rate,
+                            const int32_t* food_intake) {
+    if (!ctx || count < 0 || (count > 0 && (!ids || !coords || !dir || !speed || !speed_factor || !lag || !sample_rate || !food_intake)))
+        return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: null argument");
+    if (!ctx->slab) return fail(ctx, FISHABM_E_STATE, "fishabm_set_state_owned is for slab contexts (use fishabm_set_state)");
+    if (ctx->step_open) return fail(ctx, FISHABM_E_STATE, "a slab step is open: call fishabm_slab_end_step first");
+    if (count > ctx->n || count > ctx->cap) return fail(ctx, FISHABM_E_NOMEM, "fishabm_set_state_owned: %d fish exceed the slab's capacity %d", count, ctx->cap);
+    CK(cudaSetDevice(ctx->p.device));
+    if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    ctx->pending_sample = false;
+    for (int i = 0; i < count; ++i)
+        if (!(speed[i] * 3.0 < (double)CELL_I)) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: speed %g: slabs need 3*speed < 200", speed[i]);
+    const size_t n = (size_t)count;
+    cudaStream_t s = ctx->stream;
+    { int rcb = begin_timed(ctx); if (rcb) return rcb; }
+    CK(cudaMemcpyAsync(ctx->st_coords, coords, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_dir, dir, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_speed, speed, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_sf, speed_factor, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_lag, lag, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_rate, sample_rate, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_intake, food_intake, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->st_ids, ids, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->err, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->cell_count, 0, ((size_t)ctx->ncell + 1) * sizeof(int), s));
+    CK(cudaMemsetAsync(ctx->n_unsorted, 0, sizeof(int), s));
+    {   // 1. this slab's own fish -> sorted arrays (no ghosts yet)
+        const Buffers& b = ctx->buf[ctx->cur];
+        IngestArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake,
+                     b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted, ctx->st_ids,
+                     count, ctx->cap, ctx->g, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+        if (count > 0) ingest_kernel<<<cdiv(count, 256), 256, 0, s>>>(a);
+        ctx->launches += 1;
+        int rc = rebuild(ctx);
+        if (rc) return rc;
+    }
+    {   // 2. boundary columns -> the neighbours' halos: one exchange, then the ordinary re-sort takes the ghosts in
+        const Buffers& b = ctx->buf[ctx->cur];
+        HaloRefreshArgs h{b.rec, b.cold1, b.cell, ctx->cell_start, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->g, {}, {}};
+        int rc = open_out_messages(ctx, &h.out_left, &h.out_right);
+        if (rc) return rc;
+        halo_refresh_kernel<<<cdiv(ctx->cap, 256), 256, 0, s>>>(h);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        unsigned char *il = nullptr, *ir = nullptr;
+        if ((rc = exchange(ctx, &il, &ir))) return rc;
+        if ((rc = finish_move(ctx, il, ir))) return rc;
+    }
+    ctx->have_state = true;  // provisional: fishabm_wait reports bad input
+    return 0;
+}
+
+int fishabm_get_state_owned(fishabm_ctx* ctx, int32_t* count, int32_t* ids, double* coords, double* dir, double* speed,
+                            double* speed_factor, int32_t* lag, int32_t* sample_rate, int32_t* food_intake) {
+    int rc = need_state(ctx);
+    if (rc) return rc;
+    if (!count) return fail(ctx, FISHABM_E_ARG, "fishabm_get_state_owned: null count");
+    if (ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_get_state_owned is for single schools / slabs");
+    CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    int cnt = 0;
+    if ((rc = owned_range(ctx, &cnt))) return rc;
+    if (cnt > *count) { const int have = *count; *count = cnt; return fail(ctx, FISHABM_E_NOMEM, "fishabm_get_state_owned: %d fish owned, arrays hold %d", cnt, have); }
+    *count = cnt;
+    cudaStream_t s = ctx->stream;
+    const Buffers& b = ctx->buf[ctx->cur];
+    ExportArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start,
+                 coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr, speed ? ctx->st_speed : nullptr,
+                 speed_factor ? ctx->st_sf : nullptr, lag ? ctx->st_lag : nullptr, sample_rate ? ctx->st_rate : nullptr,
+                 food_intake ? ctx->st_intake : nullptr, ids ? ctx->st_ids : nullptr, ctx->g, 1};
+    if (cnt > 0) export_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(a);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    const size_t n = (size_t)cnt;
+    if (ids) CK(cudaMemcpyAsync(ids, ctx->st_ids, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (speed) CK(cudaMemcpyAsync(speed, ctx->st_speed, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (speed_factor) CK(cudaMemcpyAsync(speed_factor, ctx->st_sf, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (lag) CK(cudaMemcpyAsync(lag, ctx->st_lag, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (sample_rate) CK(cudaMemcpyAsync(sample_rate, ctx->st_rate, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (food_intake) CK(cudaMemcpyAsync(food_intake, ctx->st_intake, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return 0;
 }
 

@@ -673,6 +673,25 @@ __global__ void apply_quality_updates_kernel(uint8_t* quality, int* upd_count, c
 }
 __global__ void reset_counter_kernel(int* p) { *p = 0; }
 
+// Slab-local set_state: every slab holds only its own fish; this pass keeps them where they are, drops stale ghosts
+// and packs the boundary columns as the neighbours' halos (the same message a move() sends, without migrants).
+struct HaloRefreshArgs {
+    const float4* rec; const int4* cold1; const int* cell; const int* cell_start;
+    int* next_cell; int* next_rank; int* next_count;
+    Grid g;
+    SlabMsg out_left, out_right;
+};
+__global__ void __launch_bounds__(256) halo_refresh_kernel(const HaloRefreshArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.cell_start[a.g.ncell]) return;
+    if (i < a.cell_start[a.g.own_c0] || i >= a.cell_start[a.g.own_c1]) { a.next_cell[i] = -1; return; }
+    const int c = a.cell[i], cx = c / a.g.ny, cy = c % a.g.ny;
+    a.next_cell[i] = c;
+    a.next_rank[i] = atomicAdd(&a.next_count[c], 1);
+    if (cx == 1) slab_push_ghost(a.out_left, a.rec[i], a.cold1[i].w, cy);
+    if (cx == a.g.lnx - 2) slab_push_ghost(a.out_right, a.rec[i], a.cold1[i].w, cy);
+}
+
 // After the exchange: the two received messages become unsorted entries behind the fish already held
 // (left neighbour's migrants -> my first owned column, its ghosts -> my left halo; mirrored for the right).
 struct IncomingArgs {
@@ -726,6 +745,7 @@ struct IngestArgs {
     float4* rec; float4* cold0; int4* cold1;
     int* next_cell; int* next_rank; int* next_count;
     int* n_unsorted;  // entry counter (atomic); a fish of a slab's edge columns can be held twice (owned + ghost)
+    const int* ids;   // null: fish i has id i (whole-school arrays); else the arrays are this slab's own fish only
     int n_global, cap_total;
     Grid g;
     int* bad;  // set to 1 if a coordinate is outside [0,W] x [0,H] or not finite, 2 if the arrays overflow
@@ -757,14 +777,17 @@ __global__ void ingest_kernel(const IngestArgs a) {
     const float dirf = (float)a.dir[i];
     double sn, cs;
     sincospi((double)dirf / 180.0, &sn, &cs);
+    const int id = a.ids ? a.ids[i] : i;
     const float4 r = make_float4(ox, oy, (float)cs, (float)sn);
     const float4 c0 = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
-    const int4 c1 = make_int4(a.lag[i], a.rate[i], a.intake[i], i);
+    const int4 c1 = make_int4(a.lag[i], a.rate[i], a.intake[i], id);
     if (a.g.wrap_x) { ingest_entry(a, i, cx, cy, r, c0, c1); return; }  // whole school: entry i, n_unsorted preset to n
     // slab: local column of the fish's global column, as an owned entry and/or as a ghost of either halo column
     int lo = cx - a.g.gx0 - 1; if (lo < 0) lo += a.g.nx_g;  // columns past the first owned one
     lo += 1;
     if (lo <= a.g.lnx - 2) ingest_entry(a, -1, lo, cy, r, c0, c1);
+    else if (a.ids) atomicOr(a.bad, 4);  // slab-local input: the fish is not in this slab's columns
+    if (a.ids) return;                   // halos come from the neighbours (halo_refresh_kernel + exchange)
     const int4 g1 = make_int4(0x7FFFFFFF, 0, 0, i);
     if (cx == a.g.gx0) ingest_entry(a, -1, 0, cy, r, c0, g1);
     if (cx == (a.g.gx0 + a.g.lnx - 1) % a.g.nx_g) ingest_entry(a, -1, a.g.lnx - 1, cy, r, c0, g1);
@@ -865,6 +888,7 @@ struct ExportArgs {
     Grid g;
     int compact;
 };
+__global__ void copy_int_kernel(const int* src, int* dst) { *dst = *src; }
 __global__ void export_kernel(const ExportArgs a) {
     const int own_b = a.cell_start[a.g.own_c0];
     const int i = own_b + blockIdx.x * blockDim.x + threadIdx.x;

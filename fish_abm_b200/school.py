@@ -81,6 +81,29 @@ class School:
                                           _p(sample_rate), _p(food_intake)))
 
     NOT_OWNED = np.iinfo(np.int32).min
+    FIELDS = ("coords", "dir", "speed", "speed_factor", "lag", "sample_rate", "food_intake")
+
+    def set_state_owned(self, ids, coords, dir, speed, speed_factor, lag, sample_rate, food_intake, wait: bool = True):
+        """slab-local set_state: only this slab's own fish (global ids `ids`); collective over the slabs.  wait=False only
+        enqueues (several slabs driven from one process: enqueue all, then wait() each)."""
+        f = lambda a: np.ascontiguousarray(a, np.float64)
+        i = lambda a: np.ascontiguousarray(a, np.int32)
+        ids = i(ids)
+        args = (ids, f(coords).reshape(-1, 2), f(dir), f(speed), f(speed_factor), i(lag), i(sample_rate), i(food_intake))
+        self._keep = args  # the copies are asynchronous: keep the host arrays alive until wait()
+        self._ck(self.L.fishabm_set_state_owned(self.ctx, len(ids), *(_p(a) for a in args)))
+        if wait:
+            self.wait()
+
+    def get_state_owned(self, out: dict | None = None) -> dict:
+        """the fish this slab (or school) owns now: compact arrays plus their global ids"""
+        n = self.n
+        if out is None:
+            out = dict(ids=np.empty(n, np.int32), coords=np.empty((n, 2)), dir=np.empty(n), speed=np.empty(n), speed_factor=np.empty(n),
+                       lag=np.empty(n, np.int32), sample_rate=np.empty(n, np.int32), food_intake=np.empty(n, np.int32))
+        cnt = C.c_int32(len(out["ids"]))
+        self._ck(self.L.fishabm_get_state_owned(self.ctx, C.byref(cnt), _p(out["ids"]), *(_p(out[k]) for k in self.FIELDS)))
+        return {k: v[:cnt.value] for k, v in out.items()}
 
     def get_state(self) -> dict:
         """Whole school: every fish.  Slab: only the entries of the fish this slab owns are written; the others keep

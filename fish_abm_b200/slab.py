@@ -263,23 +263,34 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
     cs = c.clone(); dist.all_reduce(cs, op=dist.ReduceOp.SUM)
     cm = c.clone(); dist.all_reduce(cm, op=dist.ReduceOp.MAX)
 
-    # end to end: host arrays in, host arrays out, every step (rank-local H2D of the whole-school arrays is what the
-    # C ABI's set_state takes; D2H returns the owned fish)
-    e2e_steps = 2
-    g = None
+    # end to end through the C ABI, host buffers (pinned) in and out every step: each rank uploads ITS fish
+    # (fishabm_set_state_owned: ids + state, then one halo exchange), steps, downloads its fish (which migration has
+    # changed) and its partial food sum.  No rank ever holds the whole school.
+    e2e_steps = max(3, min(args.steps, 10))
+    cap = int(info["capacity"])
+    shapes = dict(ids=((cap,), np.int32), coords=((cap, 2), np.float64), dir=((cap,), np.float64), speed=((cap,), np.float64),
+                  speed_factor=((cap,), np.float64), lag=((cap,), np.int32), sample_rate=((cap,), np.int32), food_intake=((cap,), np.int32))
+    bufs = [{k: torch.empty(shp, dtype=torch.from_numpy(np.empty(0, dt)).dtype).pin_memory().numpy() for k, (shp, dt) in shapes.items()} for _ in range(2)]
+    own = S.get_state_owned(out=bufs[0])
+    S.set_state_owned(**own)
+    S.step(1)
+    own = S.get_state_owned(out=bufs[1])
+    moved_bytes = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        S.set_state(**d)
+    for it in range(e2e_steps):
+        S.set_state_owned(**own)
         S.step(1)
-        g = S.get_state()
+        moved_bytes += 56 * len(own["ids"])
+        own = S.get_state_owned(out=bufs[it & 1])
         S.sum_array()
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    h2d = sum(v.nbytes for v in d.values())
-    d2h = int(info["owned"]) * 52 + 8
+    te = torch.tensor([e2e_s, moved_bytes / e2e_steps], dtype=torch.float64, device="cuda")
+    tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = te.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    te = tmax
+    h2d = d2h = int(float(tsum[1]))
     S.close()
     if rank == 0:
         peaks, how = measured_peaks()
@@ -291,14 +302,14 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
         line = {"metric": "agent_steps_per_sec", "value": n * args.steps / (ms_max * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C4: N={n} school, W=H={w} periodic, {world} x-slabs with 200-unit halos + migration over NCCL, "
+                "config": {"workload": f"C4: N={n} school, W=H={w} periodic, {world} x-slabs with 200-unit halos + migration ({S.transport} transport), "
                                        f"cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0" if n == N_C4 else f"N={n}, W=H={w}, {world} slabs",
                            "n_fish": n, "world": w, "parallelism": f"slab{world}", "l2": "per-rank state larger than L2" if n // world * 76 > (126 << 20) else "state fits L2, not flushed",
                            "timing": "CUDA events on each rank's library stream around fishabm_step(K) + the trailing sample pass, max over ranks",
                            "message_bytes_per_neighbour_per_step": info["message_bytes"], "wall_ms_per_step_max": wall_max / args.steps},
                 "clocks": clk, "gpu_launches": int(cs[3]),
-                "e2e": {"value": n * e2e_steps / float(te[0]), "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(float(cs[6])) * 52 + 8 * world,
-                        "steps": e2e_steps, "api": "per rank: fishabm_set_state(whole-school host arrays) + fishabm_step(1) + fishabm_get_state(owned fish) + fishabm_sum_quality"},
+                "e2e": {"value": n * e2e_steps / float(te[0]), "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h) + 8 * world,
+                        "steps": e2e_steps, "api": "per rank: fishabm_set_state_owned(its fish, pinned host arrays) + halo exchange + fishabm_step(1) + fishabm_get_state_owned + fishabm_sum_quality"},
                 "roofline": {"bound": "fp32", "kernel": "neighbour_kernel_v2", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp32_peak, "traffic": None, "per": "rank (slowest rank's launch time, mean rank's pairs)",
                              "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock)", "flops_per_launch": flops,

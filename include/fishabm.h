@@ -212,6 +212,17 @@ typedef struct fishabm_slab_endpoint {
 } fishabm_slab_endpoint;
 int fishabm_slab_get_endpoint(fishabm_ctx* ctx, fishabm_slab_endpoint* out);
 int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, const fishabm_slab_endpoint* right);
+/* Slab-local state (what a rank of a large run should use: no rank ever holds the whole school).
+ * fishabm_set_state_owned: `count` fish with global ids ids[], every one inside this slab's columns (x in
+ * [col0*200, col1*200)); afterwards the slabs refresh each other's halo columns with one exchange.  Collective over
+ * all ranks; the call only ENQUEUES (so that several slabs of one process can be driven in turn): follow it with
+ * fishabm_wait, which also reports bad input.  fishabm_get_state_owned: the fish this slab owns now, compact, with
+ * their ids; *count is the capacity of the arrays on entry and the number of fish on return. */
+int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids, const double* coords, const double* dir,
+                            const double* speed, const double* speed_factor, const int32_t* lag, const int32_t* sample_rate,
+                            const int32_t* food_intake);
+int fishabm_get_state_owned(fishabm_ctx* ctx, int32_t* count, int32_t* ids, double* coords, double* dir, double* speed,
+                            double* speed_factor, int32_t* lag, int32_t* sample_rate, int32_t* food_intake);
 /* fishabm_step without the final host synchronisation, and the matching wait (several contexts of one process that
  * are each other's neighbours must all be enqueued before any of them can finish) */
 int fishabm_step_enqueue(fishabm_ctx* ctx, int32_t nsteps);

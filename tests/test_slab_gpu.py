@@ -89,6 +89,51 @@ def test_peer_memory_transport_in_one_process(q100, nslabs, monkeypatch):
         assert np.array_equal(P.social_turn(), turn)
 
 
+def test_slab_local_state_round_trip_and_halo_refresh(q100, monkeypatch):
+    """set_state_owned / get_state_owned: every slab is given only its own fish, the halos come from one exchange; the
+    run must continue exactly like the whole school"""
+    from fish_abm_b200 import FishAbmError
+    monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "4000")
+    n, w = 30_000, 7 * 200 * 2
+    d = synth.uniform_state(n, w, w, seed=49, speed=12.0)
+    q = synth.tile_quality(q100, w, w)
+    _, g10, _, _, _ = whole_school(n, w, d, q, 80, 10)
+    _, g20, qa20, zc20, turn20 = whole_school(n, w, d, q, 80, 20)
+    with LocalSlabs(3, transport="p2p", n=n, w=w, h=w, seed=80) as P:
+        P.set_state(**d)
+        P.set_quality(q)
+        P.step(10)
+        parts = [s.get_state_owned() for s in P.S]
+        assert sum(len(p["ids"]) for p in parts) == n
+        allids = np.concatenate([p["ids"] for p in parts])
+        assert np.array_equal(np.sort(allids), np.arange(n))
+        for k in FIELDS:  # compact + ids == the whole-school state after 10 steps
+            full = np.concatenate([p[k] for p in parts])
+            assert np.array_equal(full[np.argsort(allids)], g10[k]), k
+        # hand every slab its own fish back (shuffled), halos are rebuilt by the exchange, and go on
+        rng = np.random.default_rng(0)
+        for s, p in zip(P.S, parts):
+            perm = rng.permutation(len(p["ids"]))
+            s.set_state_owned(**{k: v[perm] for k, v in p.items()}, wait=False)
+        for s in P.S:
+            s.wait()
+            s.step_index = 10
+        P.step(10)
+        assert_same(P.get_state(), g20)
+        assert np.array_equal(P.get_quality(), qa20)
+        assert np.array_equal(P.zone_counts(), zc20)
+        assert np.array_equal(P.social_turn(), turn20)
+        # a fish outside the slab's columns is refused
+        wrong = {k: v.copy() for k, v in parts[1].items()}
+        P.S[0].set_state_owned(**{k: v[:1] for k, v in wrong.items()}, wait=False)
+        P.S[1].set_state_owned(**parts[1], wait=False)
+        P.S[2].set_state_owned(**parts[2], wait=False)
+        with pytest.raises(FishAbmError) as e:
+            P.S[0].wait()
+        assert "outside this slab's columns" in str(e.value)
+        P.S[1].wait(); P.S[2].wait()
+
+
 def test_peer_memory_timeout_is_reported_not_hung(q100, monkeypatch):
     """a neighbour that never steps: the wait kernel gives up after the timeout and the call reports it"""
     from fish_abm_b200 import FishAbmError
