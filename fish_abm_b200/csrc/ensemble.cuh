@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(ENS_THREADS) ensemble_kernel(const EnsembleArg
                 float4 r = s_rec[i];
                 int cx = c1.w / a.ny, cy = c1.w % a.ny;
                 const bool moving = c1.x == 0;
-                move_core(r, c0, c1.x, cx, cy, moving ? s_turn[i] : 0.f, moving ? s_cnt[i].w : 0, err, a.rolling, a.speed_norm);
+                move_core(r, c0, c1.x, cx, cy, moving ? s_turn[i] : 0.f, moving ? s_cnt[i].w : 0, err, a.rolling, (float)(2.0 / a.speed_norm));
                 cx %= a.nx; if (cx < 0) cx += a.nx;
                 cy %= a.ny; if (cy < 0) cy += a.ny;
                 c1.w = cx * a.ny + cy;
@@ -222,9 +222,9 @@ __global__ void ens_ingest_kernel(const EnsIoArgs a) {
     if (cx >= a.nx) cx -= a.nx;
     if (cy >= a.ny) cy -= a.ny;
     const float dirf = (float)a.dir[i];
-    double sn, cs;
-    sincospi((double)dirf / 180.0, &sn, &cs);
-    a.rec[i] = make_float4(ox, oy, (float)cs, (float)sn);
+    float sn, cs;
+    heading_vector(dirf, cs, sn);
+    a.rec[i] = make_float4(ox, oy, cs, sn);
     a.cold0[i] = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
     a.cold1[i] = make_int4(a.lag[i], a.rate[i], a.intake[i], cx * a.ny + cy);
 }

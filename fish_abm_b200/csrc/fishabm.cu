@@ -87,7 +87,8 @@ struct fishabm_ctx {
     float* turn = nullptr;
     uint32_t* aux = nullptr;
     uint8_t* quality = nullptr;
-    int *upd_count = nullptr, *upd_idx = nullptr;
+    int *upd_count = nullptr, *upd_idx = nullptr;  // upd_count[2]: alternate by sample(), each apply clears the other
+    int upd_parity = 0, wc_parity = 0;
     uint8_t* upd_val = nullptr;
     unsigned long long* stats = nullptr;  // 4 pass counters + 1 scratch for sums
     int* work_counter = nullptr;
@@ -197,7 +198,8 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.g = ctx->g;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = ctx->p.replicate0;
-    a.work_counter = ctx->work_counter;
+    a.work_counter = ctx->work_counter + ctx->wc_parity;            // the persistent kernel's two cell counters alternate:
+    a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -216,7 +218,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
     } else {
-        CK(cudaMemsetAsync(ctx->work_counter, 0, sizeof(int), ctx->stream));
+        ctx->wc_parity ^= 1;
         const int grid = std::min(ctx->nb_grid, cdiv(own_cells, V2_WARPS));
         if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
         else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
@@ -250,20 +252,21 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.rec = b.rec; u.cold0 = b.cold0; u.cold1 = b.cold1; u.cell = b.cell; u.cell_start = ctx->cell_start;
     u.cnt = ctx->cnt; u.turn = ctx->turn; u.aux = ctx->aux;
     u.next_cell = ctx->next_cell; u.next_rank = ctx->next_rank; u.next_count = ctx->cell_count;
-    u.quality = ctx->quality; u.upd_count = ctx->upd_count; u.upd_idx = ctx->upd_idx; u.upd_val = ctx->upd_val;
+    const int up = ctx->upd_parity;
+    u.quality = ctx->quality; u.upd_count = ctx->upd_count + up; u.upd_idx = ctx->upd_idx; u.upd_val = ctx->upd_val;
     u.err = ctx->err;
     u.g = ctx->g; u.qcols = ctx->qcols;
     u.do_sample = do_sample; u.do_move = do_move; u.rolling = ctx->p.rolling;
-    u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = ctx->p.replicate0; u.speed_norm = ctx->speed_norm;
+    u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = ctx->p.replicate0; u.speed_norm_inv2 = (float)(2.0 / ctx->speed_norm);
     u.slab = ctx->slab ? 1 : 0;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
     if (do_sample) {
-        apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count, ctx->upd_idx, ctx->upd_val);
-        reset_counter_kernel<<<1, 1, 0, ctx->stream>>>(ctx->upd_count);
-        ctx->launches += 2;
+        apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + up, ctx->upd_count + (up ^ 1), ctx->upd_idx, ctx->upd_val);
+        ctx->upd_parity ^= 1;
+        ctx->launches += 1;
     }
     CK(cudaGetLastError());
     return 0;
@@ -555,8 +558,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->tile_sums, (size_t)cdiv(c->ncell, SCAN_TILE) + 1));
     A(dalloc(&c->cnt, cap)); A(dalloc(&c->turn, cap)); A(dalloc(&c->aux, cap));
     A(dalloc(&c->quality, nq));
-    A(dalloc(&c->upd_count, 1)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
-    A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 1)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
+    A(dalloc(&c->upd_count, 2)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
+    A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 2)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
     A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
@@ -573,7 +576,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(cudaMemset(c->cell_count, 0, ((size_t)c->ncell + 1) * sizeof(int)));
         A(cudaMemset(c->cell_start, 0, ((size_t)c->ncell + 1) * sizeof(int)));
         A(cudaMemset(c->quality, 0, nq));
-        A(cudaMemset(c->upd_count, 0, sizeof(int)));
+        A(cudaMemset(c->upd_count, 0, 2 * sizeof(int)));
+        A(cudaMemset(c->work_counter, 0, 2 * sizeof(int)));
         A(cudaMemset(c->err, 0, sizeof(int)));
         A(cudaMemset(c->stats, 0, 8 * sizeof(unsigned long long)));
         A(cudaMemset(c->aux, 0, cap * sizeof(uint32_t)));

@@ -74,7 +74,8 @@ struct NeighArgs {
     uint32_t step_sample, step_move;
     uint64_t seed;
     uint32_t replicate;
-    int* work_counter;           // zeroed before each launch of the persistent (v2) kernel
+    int* work_counter;           // cell dispenser of the persistent (v2) kernel, zero at launch
+    int* work_counter_next;      // the other dispenser: cleared by this launch for the next one
 };
 
 // aux bits
@@ -307,35 +308,42 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     return unc;
 }
 
+// heading unit vector of a stored heading (degrees, fp32): THE one place it is computed, so that a state that went
+// through get_state / set_state continues bit-identically to one that stayed on the device
+__device__ __forceinline__ void heading_vector(float dir_deg, float& cs, float& sn) { sincospif(dir_deg / 180.f, &sn, &cs); }
+
 // move() for one fish (fish_mod.cpp:165-179) in cell/offset form.  In: record, cold state, cell (cx,cy), social turn,
 // front count, the error draw.  Out: the new record / heading / speed_factor and the UNWRAPPED new cell (the caller
 // applies the world's periodicity).
 __device__ __forceinline__ void move_core(float4& r, float4& c0, int lag, int& cx, int& cy, float turn, int front, int err, int rolling,
-                                          double speed_norm) {
-    double dir = (double)c0.x;
+                                          float speed_norm_inv2) {
+    // fp32 throughout: the state is fp32 (heading ulp 3e-5 deg = 5e-7 rad, in-cell offset ulp 1.5e-5), so each result is
+    // within one ulp of the fp64 evaluation -- far inside the 1e-5 rad / 1e-4 unit parity bars -- at a fraction of
+    // the instructions of the fp64 sincospi / floor
+    float dir = c0.x;
     if (lag == 0) {
-        double d0 = dir;
-        if (d0 < 0) d0 += 360.0; else if (d0 >= 360.0) d0 -= 360.0;  // correctangle, :410-418
-        dir = d0 + ((double)turn + (double)err);
-        double sn, cs;
-        sincospi(dir / 180.0, &sn, &cs);
-        const double stepl = (double)c0.y * (double)c0.z;  // speed * OLD speed_factor (:171-172)
-        const double px = (double)r.x + stepl * cs, py = (double)r.y + stepl * sn;
-        if (rolling) c0.z = (float)(1.0 + 2.0 * (double)front / speed_norm);  // get_speed, :588-591
+        float d0 = dir;
+        if (d0 < 0.f) d0 += 360.f; else if (d0 >= 360.f) d0 -= 360.f;  // correctangle, :410-418
+        dir = d0 + (turn + (float)err);                                 // turn = social + error (:167), dir += turn (:169)
+        float sn, cs;
+        sincospif(dir / 180.f, &sn, &cs);
+        const float stepl = c0.y * c0.z;  // speed * OLD speed_factor (:171-172)
+        const float px = fmaf(stepl, cs, r.x), py = fmaf(stepl, sn, r.y);
+        if (rolling) c0.z = fmaf((float)front, speed_norm_inv2, 1.0f);  // get_speed: 1 + 2*count/num, :588-591
         // periodic wrap (correct_coords, :466-480) in cell/offset form
-        const double kx = floor(px / (double)CELL_I), ky = floor(py / (double)CELL_I);
-        float ox = (float)(px - kx * CELL_I), oy = (float)(py - ky * CELL_I);
+        const float kx = floorf(px / CELL_F), ky = floorf(py / CELL_F);
+        float ox = px - kx * CELL_F, oy = py - ky * CELL_F;
         cx += (int)kx; cy += (int)ky;
         if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
         if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
+        if (ox < 0.f) { ox += CELL_F; cx -= 1; }
+        if (oy < 0.f) { oy += CELL_F; cy -= 1; }
         r.x = ox; r.y = oy;
     } else {
-        dir = dir + (double)err;  // :177-179
+        dir = dir + (float)err;  // :177-179
     }
-    c0.x = (float)dir;
-    double sn, cs;
-    sincospi((double)c0.x / 180.0, &sn, &cs);
-    r.z = (float)cs; r.w = (float)sn;
+    c0.x = dir;
+    heading_vector(dir, r.z, r.w);
 }
 
 template <bool STATS>
@@ -557,7 +565,7 @@ struct UpdateArgs {
     uint32_t step_move;
     uint64_t seed;
     uint32_t replicate;
-    double speed_norm;
+    float speed_norm_inv2;   // 2 / num (get_speed's normaliser, fish_mod.cpp:590)
     int slab;           // pack migrants / ghosts for the two neighbours
     SlabMsg out_left, out_right;
 };
@@ -646,7 +654,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
         float4 r = a.rec[i];
         int cx = mycell / ny, cy = mycell % ny;
         const bool moving = c1.x == 0;
-        move_core(r, c0, c1.x, cx, cy, moving ? a.turn[i] : 0.f, moving ? a.cnt[i].w : 0, err, a.rolling, a.speed_norm);
+        move_core(r, c0, c1.x, cx, cy, moving ? a.turn[i] : 0.f, moving ? a.cnt[i].w : 0, err, a.rolling, a.speed_norm_inv2);
         if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
         else if (cx < 0 || cx >= a.g.lnx) { atomicOr(a.err, ERR_STEP_TOO_LONG); cx = max(0, min(cx, a.g.lnx - 1)); }
         cy %= ny; if (cy < 0) cy += ny;
@@ -667,11 +675,12 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     a.cold1[i] = c1;
 }
 
-__global__ void apply_quality_updates_kernel(uint8_t* quality, int* upd_count, const int* upd_idx, const uint8_t* upd_val) {
+// the deferred food-grid writes of one sample(); also clears the OTHER update counter (the two alternate by step)
+__global__ void apply_quality_updates_kernel(uint8_t* quality, const int* upd_count, int* upd_count_next, const int* upd_idx, const uint8_t* upd_val) {
     const int n = *upd_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *upd_count_next = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) quality[upd_idx[k]] = upd_val[k];
 }
-__global__ void reset_counter_kernel(int* p) { *p = 0; }
 
 // Slab-local set_state: every slab holds only its own fish; this pass keeps them where they are, drops stale ghosts
 // and packs the boundary columns as the neighbours' halos (the same message a move() sends, without migrants).
@@ -775,10 +784,10 @@ __global__ void ingest_kernel(const IngestArgs a) {
     if (cx >= a.g.nx_g) cx -= a.g.nx_g;
     if (cy >= a.g.ny) cy -= a.g.ny;
     const float dirf = (float)a.dir[i];
-    double sn, cs;
-    sincospi((double)dirf / 180.0, &sn, &cs);
+    float sn, cs;
+    heading_vector(dirf, cs, sn);
     const int id = a.ids ? a.ids[i] : i;
-    const float4 r = make_float4(ox, oy, (float)cs, (float)sn);
+    const float4 r = make_float4(ox, oy, cs, sn);
     const float4 c0 = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
     const int4 c1 = make_int4(a.lag[i], a.rate[i], a.intake[i], id);
     if (a.g.wrap_x) { ingest_entry(a, i, cx, cy, r, c0, c1); return; }  // whole school: entry i, n_unsorted preset to n

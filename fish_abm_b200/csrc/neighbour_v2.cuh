@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
     V2WarpSmem& S = reinterpret_cast<V2WarpSmem*>(v2_smem_raw)[warp];
 
     unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.work_counter_next = 0;
     while (true) {  // persistent warps: cells are handed out in order by an atomic counter
         int c = 0;
         if (lane == 0) c = atomicAdd(a.work_counter, 1);
