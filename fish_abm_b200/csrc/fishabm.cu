@@ -89,6 +89,8 @@ struct fishabm_ctx {
     uint8_t* quality = nullptr;
     int *upd_count = nullptr, *upd_idx = nullptr;  // upd_count[2]: alternate by sample(), each apply clears the other
     int upd_parity = 0, wc_parity = 0;
+    int* scan_sync = nullptr;   // [2] ticket + epoch flag of the fused scan
+    int scan_epoch = 0, scan_resident = 0;
     uint8_t* upd_val = nullptr;
     unsigned long long* stats = nullptr;  // 4 pass counters + 1 scratch for sums
     int* work_counter = nullptr;
@@ -174,9 +176,15 @@ size_t inbox_flag_off(const fishabm_ctx* c, int side, int slot) { return 4 * c->
 // ---- the counting sort: counts (already accumulated in cell_count) -> cell_start; scatter cur -> other
 int rebuild(fishabm_ctx* ctx) {
     const int ntiles = cdiv(ctx->ncell, SCAN_TILE);
-    scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums);
-    scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, ntiles);
-    scan_finish_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start);
+    if (ntiles <= ctx->scan_resident) {  // every tile's block is resident at once: one launch
+        ScanFusedArgs f{ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start, ctx->scan_sync, ctx->scan_sync + 1, ++ctx->scan_epoch, ntiles};
+        scan_fused_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(f);
+        ctx->launches -= 2;
+    } else {
+        scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums);
+        scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, ntiles);
+        scan_finish_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start);
+    }
     const Buffers& in = ctx->buf[ctx->cur];
     const Buffers& out = ctx->buf[ctx->cur ^ 1];
     ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap};
@@ -560,7 +568,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->quality, nq));
     A(dalloc(&c->upd_count, 2)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
     A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 2)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
-    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R));
+    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R)); A(dalloc(&c->scan_sync, 2));
+    if (ok) A(cudaMemset(c->scan_sync, 0, 2 * sizeof(int)));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
     if (c->slab) {
@@ -596,6 +605,9 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
         c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
+        int scan_per_sm = 0;
+        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_per_sm, scan_fused_kernel, SCAN_THREADS, 0));
+        c->scan_resident = scan_per_sm * sms / 2;  // the fused scan spins on a flag: only with every block resident, with margin
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");
     if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
@@ -621,7 +633,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
-    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums);
+    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums); cudaFree(c->scan_sync);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
     cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);

@@ -869,6 +869,56 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_finish_kernel(int* __restri
     if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) start[n] = run;
 }
 
+// the three passes in ONE launch, for grids whose tiles are all co-resident (the host checks): every block publishes
+// its tile sum and takes a ticket; the last block to arrive scans the tile sums and raises the epoch flag; the others
+// wait for it and finish their tile.  Saves two launches (~7 us) per step.
+struct ScanFusedArgs { int* count; int n; int* tile_sums; int* start; int* ticket; int* ready; int epoch; int ntiles; };
+__global__ void __launch_bounds__(SCAN_THREADS) scan_fused_kernel(const ScanFusedArgs a) {
+    __shared__ int s_warp[33];
+    __shared__ int s_last;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int vals[SCAN_ITEMS];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { vals[k] = (base + k < a.n) ? a.count[base + k] : 0; v += vals[k]; }
+    int total;
+    const int ex = block_exclusive_scan(v, &total, s_warp);
+    if (threadIdx.x == 0) {
+        a.tile_sums[blockIdx.x] = total;
+        __threadfence();
+        s_last = (atomicAdd(a.ticket, 1) == a.ntiles - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {  // exclusive scan of the tile sums (any length), in place
+        __threadfence();
+        int carry = 0;
+        for (int b = 0; b < a.ntiles; b += SCAN_THREADS) {
+            const int i = b + threadIdx.x;
+            const int t = i < a.ntiles ? *reinterpret_cast<volatile int*>(&a.tile_sums[i]) : 0;
+            int tot;
+            const int e = block_exclusive_scan(t, &tot, s_warp);
+            if (i < a.ntiles) a.tile_sums[i] = carry + e;
+            carry += tot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *a.ticket = 0;
+            __threadfence();
+            *reinterpret_cast<volatile int*>(a.ready) = a.epoch;
+        }
+    }
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile int*>(a.ready) != a.epoch) __nanosleep(40);
+        __threadfence();
+    }
+    __syncthreads();
+    int run = ex + *reinterpret_cast<volatile int*>(&a.tile_sums[blockIdx.x]);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < a.n) { a.start[base + k] = run; run += vals[k]; a.count[base + k] = 0; }
+    if (base <= a.n - 1 && a.n - 1 < base + SCAN_ITEMS) a.start[a.n] = run;
+}
+
 struct ScatterArgs {
     const float4* rec_in; const float4* cold0_in; const int4* cold1_in;
     float4* rec_out; float4* cold0_out; int4* cold1_out; int* cell_out;
