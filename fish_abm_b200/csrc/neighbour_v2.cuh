@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
             if (nf == 0) continue;
             if (STATS) st_focal += (unsigned)nf;
 
+            // lane f keeps focal fish f's reduced sums of the current batch in registers; shared-memory accumulators are
+            // only touched when the stencil needs more than one window batch
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, mfar = 0, mnear = 0, mties = 0;
             for (int b = 0; b < nbatch; ++b) {
                 const int fill = (staged == b) ? min(T - b * V2_WIN, V2_WIN) : stage(b);
                 const int nch = (fill + 31) >> 5;
@@ -207,21 +210,21 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
                     const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
                     const int tsum = __any_sync(FULL, P.ties != 0) ? __reduce_add_sync(FULL, P.ties) : 0;
                     if (STATS) st_inter += (unsigned)(cfar & 0xFFFF);
-                    if (lane == 0) {
-                        const int4 cc = make_int4(cnear >> 16, cnear & 0xFFFF, cfar & 0xFFFF, cfar >> 16);
-                        if (b == 0) {
-                            S.acc[f][0] = r0; S.acc[f][1] = r1; S.acc[f][2] = r2; S.acc[f][3] = r3; S.acc[f][4] = r4; S.acc[f][5] = r5;
-                            S.cnt[f] = cc;
-                            S.fties[f] = tsum;
-                        } else {
-                            S.acc[f][0] += r0; S.acc[f][1] += r1; S.acc[f][2] += r2; S.acc[f][3] += r3; S.acc[f][4] += r4; S.acc[f][5] += r5;
-                            int4 o = S.cnt[f];
-                            o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
-                            S.cnt[f] = o;
-                            S.fties[f] += tsum;
-                        }
+                    if (lane == f) { m0 = r0; m1 = r1; m2 = r2; m3 = r3; m4 = r4; m5 = r5; mfar = cfar; mnear = cnear; mties = tsum; }
+                }
+                if (nbatch > 1 && lane < nf) {
+                    const int4 cc = make_int4(mnear >> 16, mnear & 0xFFFF, mfar & 0xFFFF, mfar >> 16);
+                    if (b == 0) {
+                        S.acc[lane][0] = m0; S.acc[lane][1] = m1; S.acc[lane][2] = m2; S.acc[lane][3] = m3; S.acc[lane][4] = m4; S.acc[lane][5] = m5;
+                        S.cnt[lane] = cc;
+                        S.fties[lane] = mties;
+                    } else {
+                        S.acc[lane][0] += m0; S.acc[lane][1] += m1; S.acc[lane][2] += m2; S.acc[lane][3] += m3; S.acc[lane][4] += m4; S.acc[lane][5] += m5;
+                        int4 o = S.cnt[lane];
+                        o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+                        S.cnt[lane] = o;
+                        S.fties[lane] += mties;
                     }
-                    __syncwarp();
                 }
             }
             // ---- epilogue, one focal fish per lane
@@ -229,9 +232,14 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
             if (lane < nf) {
                 const int idx = S.fidx[lane];
                 const int4 k1 = a.cold1[idx];
-                const int4 cc = S.cnt[lane];
                 const float4 F = S.frec[lane];
-                finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], S.fties[lane]);
+                if (nbatch > 1) {
+                    const int4 cc = S.cnt[lane];
+                    finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], S.fties[lane]);
+                } else {
+                    const long long sums[6] = {m0, m1, m2, m3, m4, m5};
+                    finish_focal(a, idx, k1, F.x, F.y, mnear >> 16, mnear & 0xFFFF, mfar & 0xFFFF, mfar >> 16, sums, mties);
+                }
             }
             __syncwarp();
         }
