@@ -86,6 +86,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_capture(kernel_prefix: str):
+    """the committed `ncu --set full` capture of the dominant kernel (profiles/neighbour_ncu.json, written by
+    tools/ncu_to_json.py from the capture named inside): DRAM traffic per launch and pipe / issue utilisation"""
+    p = os.path.join(ROOT, "profiles", "neighbour_ncu.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    for k in d.get("launches", []):
+        if k.get("kernel", "").startswith(kernel_prefix):
+            return dict(k, source="profiles/neighbour_ncu.json <- " + d.get("source", "?"))
+    return None
+
+
 def flops_alg(cand: float, inter: float) -> float:
     """13 flops per candidate pair + 20 per interacting pair"""
     return 13.0 * cand + 20.0 * inter
@@ -220,8 +234,13 @@ def ours(args, rank: int, world: int, local_rank: int):
     fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     per_launch_ms = nb_ms / max(nb_launches, 1)
     achieved = flops_alg(cand, inter) / (per_launch_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32", "kernel": "neighbour_kernel", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp32_peak, "traffic": None,
+    cap = ncu_capture("neighbour_kernel_v2")
+    roofline = {"bound": "fp32", "kernel": "neighbour_kernel_v2", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak, "traffic": cap["dram_bytes"] if cap else None,
+                "traffic_note": "ncu dram__bytes_read+write of one launch (the 1M-fish state is L2-resident: 16 B x 1M hot records)" if cap else None,
+                "ncu": {k: cap[k] for k in ("issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct", "warp_instructions", "registers", "source") if k in cap} if cap else None,
+                "binding_limit": "instruction issue: the pair loop needs ~100 issued instructions per interacting pair (compares, selects, "
+                                 "ballots, polynomial atan2, MUFU) of which SURVEY 8(d)'s convention counts 20 flops; see DESIGN.md section 3",
                 "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock); FP32 is not in MEASURED_PEAKS.json",
                 "flops_per_launch": flops_alg(cand, inter), "candidates_per_launch": cand, "interacting_per_launch": inter,
                 "focal_per_launch": focal, "launch_ms": per_launch_ms, "share_of_step": nb_ms / total_ms}
@@ -276,6 +295,61 @@ def ours(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
 
 
+def ensemble_leg(args, rank: int, world: int, local_rank: int):
+    """BASELINE.json configs[4]: 65,536 replicate schools of N=200 (speed sweep 2.5..20 as in data/), replicates split
+    across the GPUs with no communication (weak scaling in the contract's sense: nothing is exchanged).  Not the
+    headline line; run with --workload ensemble."""
+    import torch
+    from fish_abm_b200 import Ensemble
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total, n = args.schools, 200
+    r0, r1 = rank * total // world, (rank + 1) * total // world
+    R = r1 - r0
+    q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+    E = Ensemble(R, n=n, seed=0x5EED, replicate0=r0, device=local_rank, speed_norm=float(n))
+    E.initialize(5.0)
+    g = E.get_state()
+    speeds = np.array([2.5, 5, 7.5, 10, 12.5, 15, 17.5, 20])[(np.arange(r0, r1) % 8)]
+    g["speed"][:] = speeds[:, None]
+    E.set_state(**g)
+    E.set_quality(q100)
+    for _ in range(args.warmup):
+        E.step(1)
+    torch.cuda.synchronize()
+    launches0 = E.launch_count()
+    E.step(args.steps)   # K steps of every school in ONE launch: state and food grid stay in shared memory
+    ms = E.last_step_ms()
+    launches = E.launch_count() - launches0
+    t0 = time.perf_counter()
+    sumq, _ = E.run_logged(args.steps)   # e2e flavour: the same steps with the depletion log copied back to the host
+    e2e_s = time.perf_counter() - t0
+    eaten = int((3499 - np.asarray(E.sum_array())).sum())
+    E.close()
+    vals = np.array([ms, e2e_s, launches, eaten], np.float64)
+    if world > 1:
+        t = torch.tensor(vals, device="cuda")
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s, launches, eaten = float(mx[0]), float(mx[1]), int(sm[2]), int(sm[3])
+    if rank == 0:
+        line = {"metric": "agent_steps_per_sec", "value": total * n * args.steps / (ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C5: ensemble of {total} replicate schools of N={n}, 2000x2000 window each, quality.csv, speed sweep 2.5..20, "
+                                       f"{world} GPU(s), no communication", "schools": total, "n_fish": n, "l2": "state in shared memory for the whole launch"},
+                "gpu_launches": int(launches),
+                "e2e": {"value": total * n * args.steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": int(8 * total), "api": "fishabm_run_logged: K steps + sum_array per step per school copied to the host"},
+                "school_steps_per_sec": total * args.steps / (ms * 1e-3), "food_eaten": eaten, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,6 +358,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fish", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="school", choices=["school", "ensemble"])
+    ap.add_argument("--schools", type=int, default=65536)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -296,6 +372,8 @@ def main():
         if args.steps > 20:
             args.steps = 20
         return reference_arm(args, rank, world)
+    if args.workload == "ensemble":
+        return ensemble_leg(args, rank, world, local_rank)
     return ours(args, rank, world, local_rank)
 
 
