@@ -108,13 +108,26 @@ class DistributedSchool(School):
         if nranks > 1:
             import torch
             dev = torch.device("cuda", device) if dist.get_backend() == "nccl" else None
+            if self.transport != "nccl":
+                # peer memory needs CUDA IPC + peer access between ring neighbours; if ANY rank cannot attach, every
+                # rank falls back to NCCL together
+                ok = 1
+                try:
+                    eps = gather_endpoints(dist, self.slab_endpoint(), dev)
+                    left, right = ring(rank, nranks)
+                    self.slab_attach(eps[left], eps[right])
+                except Exception as e:  # noqa: BLE001
+                    ok = 0
+                    self.attach_error = str(e)
+                flag = torch.tensor([ok], dtype=torch.int32, device=dev if dev is not None else "cpu")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # also the barrier: nobody stores into an inbox before all attached
+                if int(flag.item()) == 0:
+                    if ok:  # attached here but not everywhere: a fresh context for the NCCL path
+                        self.close()
+                        School.__init__(self, rank=rank, nranks=nranks, device=device, **kw)
+                    self.transport = "nccl"
             if self.transport == "nccl":
                 self.slab_connect(broadcast_unique_id(dist, rank, dev))
-            else:
-                eps = gather_endpoints(dist, self.slab_endpoint(), dev)
-                left, right = ring(rank, nranks)
-                self.slab_attach(eps[left], eps[right])
-                dist.barrier()  # nobody starts storing into an inbox before everyone has attached
 
 
 # ---- several slabs in one process -----------------------------------------------------------------------------------------
