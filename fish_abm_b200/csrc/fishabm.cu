@@ -952,6 +952,32 @@ int fishabm_load_quality_csv(const char* path, int32_t* q, int32_t max_rows, int
     return 0;
 }
 
+int fishabm_create_environment(uint64_t seed, uint32_t replicate, int32_t n_seeds, int32_t* q, int32_t rows, int32_t cols,
+                               int32_t row_stride) {
+    // fish_mod.cpp:482-531, the sweeps exactly as written (including `quality[u][i+1]` tested for non-zero rather than
+    // `> p`, and the inclusive 0..rows / 0..cols seed ranges whose out-of-grid hits have no effect)
+    if (!q || rows < 2 || cols < 2 || row_stride < cols || n_seeds < 0) return FISHABM_E_ARG;
+    const uint32_t STREAM_QUALITY = 3, STREAM_ENV = 7;
+    uint32_t kq = 0, ke = 0;
+    auto Q = [&](int u, int i) -> int32_t& { return q[(size_t)u * row_stride + i]; };
+    for (int u = 0; u < rows; ++u)
+        for (int i = 0; i < cols; ++i) Q(u, i) = 0;
+    for (int s = 0; s < n_seeds; ++s) {
+        const int r = fishrng::draw(seed, replicate, 0, 0, STREAM_ENV, ke++, 0, rows);
+        const int c = fishrng::draw(seed, replicate, 0, 0, STREAM_ENV, ke++, 0, cols);
+        if (r < rows && c < cols) Q(r, c) = 10;
+    }
+    for (int p = 0; p < 20; ++p) {
+        for (int u = 0; u < rows - 1; ++u)
+            for (int i = 0; i < cols - 1; ++i)
+                if (Q(u + 1, i) > p || Q(u + 1, i + 1) > p || Q(u, i + 1)) Q(u, i) = fishrng::draw(seed, replicate, 0, 0, STREAM_QUALITY, kq++, 0, 10);
+        for (int u = rows - 1; u > 0; --u)
+            for (int i = cols - 1; i > 0; --i)
+                if (Q(u - 1, i) > p || Q(u - 1, i - 1) > p || Q(u, i - 1)) Q(u, i) = fishrng::draw(seed, replicate, 0, 0, STREAM_QUALITY, kq++, 0, 10);
+    }
+    return 0;
+}
+
 // ---- frozen-state queries ------------------------------------------------------------------------------
 static int export_pass(fishabm_ctx* ctx, int32_t* cnt4, double* turn, int32_t* n_avoid, int32_t* n_align, int32_t* n_attract, double* speed) {
     int rc, cnt = 0;

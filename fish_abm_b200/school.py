@@ -153,6 +153,13 @@ class School:
         self.set_quality(q)
         return q
 
+    def create_environment(self, n_seeds: int, seed: int | None = None, replicate: int = 0):
+        """create_environment(environment, quality, struc), fish_mod.cpp:482-531, with a live seed count: generates the
+        food map on the host and uploads it"""
+        q = create_environment(n_seeds, self.rows, self.cols, int(self.params.seed) if seed is None else seed, replicate)
+        self.set_quality(q)
+        return q
+
     # ---- frozen-state queries --------------------------------------------------------------------------------
     def in_zone(self, fov: int, r: float) -> np.ndarray:
         out = np.full(self.total, -1, np.int32)
@@ -322,6 +329,15 @@ def slab_unique_id() -> bytes:
     if rc != 0:
         raise FishAbmError(rc, L.fishabm_last_error(None).decode())
     return bytes(buf)
+
+
+def create_environment(n_seeds: int, rows: int = 100, cols: int = 100, seed: int = 0, replicate: int = 0) -> np.ndarray:
+    """the reference's procedural food map (fish_mod.cpp:482-531); host-side, needs no GPU"""
+    q = np.zeros((rows, cols), np.int32)
+    rc = _lib.load().fishabm_create_environment(seed, replicate, int(n_seeds), _p(q), rows, cols, cols)
+    if rc != 0:
+        raise FishAbmError(rc, "fishabm_create_environment: bad argument")
+    return q
 
 
 def averageturn(v, comb_weight: bool = False) -> float:

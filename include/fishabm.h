@@ -118,6 +118,14 @@ int fishabm_sum_quality(fishabm_ctx* ctx, int64_t* sums /* [replicates] */);
 int fishabm_load_quality_csv(const char* path, int32_t* q, int32_t max_rows, int32_t max_cols, int32_t row_stride,
                              int32_t* rows_out, int32_t* cols_out);
 
+/* create_environment(environment, quality, struc), fish_mod.cpp:482-531: a procedural food map -- n_seeds cells of
+ * quality 10 spread by 20 forward/backward sweeps that redraw a cell (0..10) whenever a lower/right (resp. upper/left)
+ * neighbour is richer than the sweep index.  The reference draws the seed count from distrib_seed(0,0), i.e. always 0
+ * (an empty map; its main() loads quality.csv instead); here it is an argument.  Host-side, one-off; draws are the
+ * k-th of their stream in call order (fish id 0, step 0).  Values reach 10: they fit the library's 8-bit grid. */
+int fishabm_create_environment(uint64_t seed, uint32_t replicate, int32_t n_seeds, int32_t* q, int32_t rows, int32_t cols,
+                               int32_t row_stride);
+
 /* ---- frozen-state queries: one result per fish, no mutation ------------------------------------------ */
 /* in_zone(inds,id,fov,r,struc) for every id, fish_mod.cpp:226-260.  r <= 200. */
 int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out);

@@ -256,6 +256,32 @@ void orc_sample(orc_school* S, uint32_t step, const int* counts_or_null) {
 }
 
 /* sum_array, fish_mod.cpp:593-601 */
+/* create_environment, fish_mod.cpp:482-531 (dead code in the reference's main: distrib_seed(0,0) gives 0 seeds; here
+ * the seed count is an argument).  Draws: the k-th draw of each stream in call order, fish id 0, step 0
+ * (stream 7 = the function's local distrib_rows / distrib_cols, range 0..rows / 0..cols INCLUSIVE as written).
+ * Seeds that land on row == rows or col == cols fall outside the grid the sweeps read and are dropped. */
+void orc_create_environment(int* q, int rows, int cols, int stride, int n_seeds, uint64_t seed, uint32_t replicate) {
+    uint32_t kq = 0, ke = 0;
+    for (int u = 0; u < rows; ++u)
+        for (int i = 0; i < cols; ++i) q[u * stride + i] = 0;
+    for (int s = 0; s < n_seeds; ++s) {
+        int r = orc_draw_from(seed, replicate, 0, 0, 7, ke++, 0, rows);
+        int c = orc_draw_from(seed, replicate, 0, 0, 7, ke++, 0, cols);
+        if (r < rows && c < cols) q[r * stride + c] = 10;
+    }
+    for (int p = 0; p < 20; ++p) {
+        for (int u = 0; u < rows; ++u)
+            for (int i = 0; i < cols; ++i)
+                if (u < rows - 1 && i < cols - 1)
+                    if (q[(u + 1) * stride + i] > p || q[(u + 1) * stride + i + 1] > p || q[u * stride + i + 1])
+                        q[u * stride + i] = orc_draw_from(seed, replicate, 0, 0, ORC_STREAM_QUALITY, kq++, 0, 10);
+        for (int u = rows - 1; u > 0; --u)
+            for (int i = cols - 1; i > 0; --i)
+                if (q[(u - 1) * stride + i] > p || q[(u - 1) * stride + i - 1] > p || q[u * stride + i - 1])
+                    q[u * stride + i] = orc_draw_from(seed, replicate, 0, 0, ORC_STREAM_QUALITY, kq++, 0, 10);
+    }
+}
+
 long orc_sum_quality(const orc_school* S) {
     long s = 0;
     for (int r = 0; r < S->rows; ++r) for (int c = 0; c < S->cols; ++c) s += S->quality[(size_t)r * S->q_stride + c];

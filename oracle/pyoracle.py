@@ -105,6 +105,8 @@ class Oracle:
             L.orc_in_zone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
             L.orc_in_zone_all.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
             L.orc_sum_quality.restype = C.c_long
+            L.orc_create_environment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32]
+            L.orc_create_environment.restype = None
             L.orc_time_focal.restype = C.c_double
             L.orc_time_focal.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
             L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
@@ -193,6 +195,12 @@ class Oracle:
     def sum_quality(self) -> int:
         s = self._s(); return int(self.L.orc_sum_quality(C.byref(s)))
 
+    @classmethod
+    def create_environment(cls, n_seeds: int, rows: int = 100, cols: int = 100, seed: int = 0, replicate: int = 0) -> np.ndarray:
+        q = np.zeros((rows, cols), np.int32)
+        cls.lib().orc_create_environment(_p(q), rows, cols, cols, int(n_seeds), C.c_uint64(seed), C.c_uint32(replicate))
+        return q
+
     def time_focal(self, ids: np.ndarray):
         ids = np.ascontiguousarray(ids, np.int32)
         s = self._s()
@@ -267,6 +275,8 @@ class RefLib:
             raise RuntimeError(f"{path} missing: run oracle/build_ref.sh {num} where /root/reference exists")
         L = C.CDLL(path)
         L.ref_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+        if hasattr(L, "ref_create_environment"):
+            L.ref_create_environment.argtypes = [C.c_int, C.c_uint64, C.c_uint32]
         L.ref_run.restype = C.c_double
         L.ref_run.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.ref_time_focal.restype = C.c_double
@@ -318,6 +328,10 @@ class RefLib:
 
     def get_environment(self, directory: str) -> int:
         return self.L.ref_get_environment(directory.encode())
+
+    def create_environment(self, n_seeds: int, seed: int, replicate: int = 0, rows: int = 100, cols: int = 100) -> np.ndarray:
+        self.L.ref_create_environment(int(n_seeds), C.c_uint64(seed), C.c_uint32(replicate))
+        return self.get_quality(rows, cols)
 
     def sum_array(self) -> int:
         return int(self.L.ref_sum_array())

@@ -49,7 +49,9 @@ enum HarnessMode {
     HM_MOVE = 1,   // inside reference move(): error draws arrive once per fish in id order
     HM_SAMPLE = 2, // inside reference sample(): sample draws arrive for lag==0 fish in id order
     HM_INIT = 3,   // inside reference initialize(): randomwalk draws arrive once per fish
-    HM_ZERO = 4    // every draw returns 0 (or `a` if 0 is outside [a,b])
+    HM_ZERO = 4,   // every draw returns 0 (or `a` if 0 is outside [a,b])
+    HM_ENV = 5     // inside reference create_environment(): distrib_seed returns env_seeds; every other draw is the
+                   // k-th of its stream (k = 0,1,2,... in call order), fish id 0
 };
 
 struct HarnessCtx {
@@ -65,6 +67,8 @@ struct HarnessCtx {
     const int* lag0_ids = nullptr;   // HM_SAMPLE: ids with lag==0 in id order
     long n_lag0 = 0;
     long census[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int env_seeds = 0;               // HM_ENV: the value distrib_seed yields (the shipped (0,0) range can only give 0)
+    long env_k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int probe_seq[4] = {-1, -1, -1, -1}; // first streams drawn since probe_n was reset
     int probe_n = 0;
 };
@@ -86,6 +90,10 @@ static int harness_draw(int a, int b) {
     c.census[stream & 7]++;
     if (c.probe_n < 4) c.probe_seq[c.probe_n++] = stream;
     if (c.mode == HM_ZERO) return (a <= 0 && 0 <= b) ? 0 : a;
+    if (c.mode == HM_ENV) {
+        if (stream == ORC_STREAM_SEED) return c.env_seeds;
+        return orc_draw_from(c.seed, c.replicate, 0, 0, (uint32_t)stream, (uint32_t)c.env_k[stream & 7]++, a, b);
+    }
     int id = c.focal;
     uint32_t k0 = 0;
     switch (stream) {
@@ -274,6 +282,21 @@ int ref_get_environment(const char* dir_with_quality_csv) {
     memset(g_quality, 0, sizeof g_quality);
     run_big(job_get_env, nullptr);
     if (chdir(old) != 0) return -3;
+    return 0;
+}
+
+// create_environment (fish_mod.cpp:482-531): dead code in the reference's main (distrib_seed(0,0) yields 0 seeds);
+// replayed here with a live seed count
+static void job_create_env(void*) { create_environment(g_env, g_quality, g_struc); }
+int ref_create_environment(int n_seeds, uint64_t seed, uint32_t replicate) {
+    memset(g_quality, 0, sizeof g_quality);
+    g_ctx = HarnessCtx();
+    g_ctx.seed = seed; g_ctx.replicate = replicate; g_ctx.mode = HM_ENV; g_ctx.env_seeds = n_seeds;
+    std::ostringstream sink;  // the reference prints progress lines
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    run_big(job_create_env, nullptr);
+    std::cout.rdbuf(old);
+    g_ctx.mode = HM_FOCAL;
     return 0;
 }
 
