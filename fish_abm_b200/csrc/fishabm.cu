@@ -206,6 +206,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.g = ctx->g;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = ctx->p.replicate0;
+    a.split = 1;
     a.work_counter = ctx->work_counter + ctx->wc_parity;            // the persistent kernel's two cell counters alternate:
     a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -227,7 +228,10 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
     } else {
         ctx->wc_parity ^= 1;
-        const int grid = std::min(ctx->nb_grid, cdiv(own_cells, V2_WARPS));
+        // fewer cells than resident warps (small or dense schools): split every cell's fish over several work items
+        a.split = std::max(1, std::min(32, (2 * ctx->nb_grid * V2_WARPS) / std::max(1, own_cells)));
+        if (const char* sp = getenv("FISHABM_SPLIT")) a.split = std::max(1, std::min(32, atoi(sp)));
+        const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V2_WARPS));
         if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
         else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
     }

@@ -55,12 +55,19 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
 
     unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.work_counter_next = 0;
-    while (true) {  // persistent warps: cells are handed out in order by an atomic counter
-        int c = 0;
-        if (lane == 0) c = atomicAdd(a.work_counter, 1);
-        c = a.g.own_c0 + __shfl_sync(FULL, c, 0);
-        if (c >= a.g.own_c1) break;
-        const int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
+    const int n_items = (a.g.own_c1 - a.g.own_c0) * a.split;
+    while (true) {  // persistent warps: work items (a cell, or one of `split` slices of a cell's fish) are handed out in order
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.work_counter, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_items) break;
+        const int c = a.g.own_c0 + t / a.split;
+        int s0 = a.cell_start[c], e0 = a.cell_start[c + 1];
+        if (a.split > 1) {  // this item's slice of the cell's fish (the whole stencil is still its candidate set)
+            const int len = (e0 - s0 + a.split - 1) / a.split, sub = t % a.split;
+            s0 = min(e0, s0 + sub * len);
+            e0 = min(e0, s0 + len);
+        }
         if (s0 == e0) continue;
 
         // ---- the stencil as one flattened run: per-cell ranges, exclusive prefix (lanes 0..8), total T
