@@ -114,12 +114,15 @@ def reference_arm(args, rank: int, world: int):
         return
     from fish_abm_b200 import synth
     from oracle.pyoracle import Oracle, RefLib, State
-    n = args.fish or N_C3
+    # the same workload as our arm: C3 (1M fish) for one GPU, C4 (16.8M fish) for several.  The compiled reference has a
+    # compile-time capacity (#define num) and passes the whole school by value on the stack, so it exists here for 1M
+    # fish; at C4 size the C restatement of the same loops (pinned against it) stands in (kind "port").
+    n = args.fish or (N_C3 if args.gpus <= 1 else N_C4)
     w = synth.world_size_for(n)
     d = synth.uniform_state(n, w, w, seed=0x5EED)
     cores = min(os.cpu_count() or 1, 32)
     kind = "reference" if (n == N_C3 and RefLib.available(N_C3)) else "port"
-    k = 2 * cores
+    k = 2 * cores if n <= N_C3 else cores
     ids = np.random.default_rng(1).choice(n, k, replace=False).astype(np.int32)
     if kind == "reference":
         R = RefLib(N_C3)
@@ -134,7 +137,8 @@ def reference_arm(args, rank: int, world: int):
     secs = [run() for _ in range(args.steps)]
     tot = float(np.sum(secs))
     value = k * args.steps / tot
-    cfg = {"workload": f"C3: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C3 else f"N={n}, W=H={w}",
+    cfg = {"workload": f"C3: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C3 else
+                       (f"C4: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C4 else f"N={n}, W=H={w}"),
            "n_fish": n, "world": w, "l2": "n/a (CPU)"}
     sample = (f"{k} focal fish per step on the full {n}-fish frozen state, each doing the reference's own per-fish work of "
               f"move()+sample() (8 all-pairs passes if lag==0 else 3); agent-steps/s = focal fish / seconds (extrapolation, "
