@@ -167,6 +167,26 @@ NcclApi& nccl() {
         if (r_ != 0) return fail(ctx, FISHABM_E_COMM, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r_) : "nccl error"); \
     } while (0)
 
+// CUDA loads kernels lazily, and loading one may have to wait for the device to go idle.  The peer-memory transport
+// keeps a kernel spinning on the device until a NEIGHBOUR's kernels have run, so a first-use load in between would
+// deadlock (until the spin's timeout).  Load every kernel of the library up front, once per device.
+cudaError_t preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaSuccess;
+    auto L = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, f); };
+    L((const void*)apply_quality_updates_kernel); L((const void*)copy_int_kernel); L((const void*)ens_broadcast_quality_kernel);
+    L((const void*)ens_export_kernel); L((const void*)ens_export_pass_kernel); L((const void*)ens_ingest_kernel);
+    L((const void*)ens_sum_quality_kernel); L((const void*)ensemble_kernel); L((const void*)export_kernel);
+    L((const void*)export_pass_kernel); L((const void*)feed_list_kernel); L((const void*)halo_refresh_kernel);
+    L((const void*)in_zone_generic_kernel); L((const void*)index_by_id_kernel); L((const void*)ingest_incoming_kernel);
+    L((const void*)ingest_kernel); L((const void*)neighbour_kernel<false>); L((const void*)neighbour_kernel<true>);
+    L((const void*)neighbour_kernel_v2<false>); L((const void*)neighbour_kernel_v2<true>); L((const void*)scan_finish_kernel);
+    L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
+    L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
+    L((const void*)sum_quality_kernel); L((const void*)update_kernel);
+    return e;
+}
+
 SlabMsg msg(const fishabm_ctx* c, unsigned char* base, SlabHeader* counters = nullptr) { return SlabMsg{base, c->cap_m, c->cap_g, counters}; }
 // inbox layout: side 0 = messages from my left neighbour, side 1 = from my right; two slots per side (alternating
 // exchanges: a neighbour may already be packing exchange s+1 while exchange s is still being ingested here)
@@ -560,6 +580,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     const size_t n = (size_t)c->n * c->R, cap = ens ? n : (size_t)c->cap, nq = (size_t)c->qrows * c->qcols * c->R;
     bool ok = true;
     auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; g_create_error = cudaGetErrorString(r); } };
+    A(preload_kernels());
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
     for (int k = 0; k < (ens ? 1 : 2) && ok; ++k) {

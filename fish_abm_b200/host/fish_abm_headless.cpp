@@ -24,7 +24,9 @@ static void usage() {
     std::puts(
         "usage: fish_abm_headless [--n 60] [--steps 500] [--speed 5] [--seed S] [--w 2000] [--h 2000] [--quality quality.csv]\n"
         "                         [--replicates 1] [--no-rolling] [--device 0] [--log-quality out.csv] [--log-intake out.csv]\n"
-        "                         [--intake-every 10] [--unfused] [--quiet]\n"
+        "                         [--intake-every 10] [--unfused] [--quiet] [--slabs K] [--devices a,b,..]\n"
+        "--slabs K splits the school into K x-slabs (one context each, on --devices or all on --device), exchanging halos and\n"
+        "migrants through peer memory; results are identical to the unsplit run\n"
         "defaults are the reference's: 60 fish, 500 steps, speed 5, 2000x2000 window (fish_mod.cpp:23,116,126,53-59)");
 }
 
@@ -33,7 +35,8 @@ int main(int argc, char** argv) {
     double speed = 5.0;
     uint64_t seed = (uint64_t)time(nullptr);  // srand(time(0)), fish_mod.cpp:102
     bool rolling = true, unfused = false, quiet = false;
-    std::string qpath = "quality.csv", log_q, log_i;
+    std::string qpath = "quality.csv", log_q, log_i, devlist;
+    int slabs = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
@@ -52,12 +55,25 @@ int main(int argc, char** argv) {
         else if (a == "--intake-every") intake_every = std::atoi(next());
         else if (a == "--unfused") unfused = true;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--slabs") slabs = std::atoi(next());
+        else if (a == "--devices") devlist = next();
         else if (a == "--help" || a == "-h") { usage(); return 0; }
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); return 2; }
     }
     try {
         Structure fish_struc(w, h);                                    // fish_mod.cpp:104
-        Backend gpu(n, fish_struc, seed, device, replicates, rolling, /*speed_norm = num*/ (double)n);
+        std::vector<int> slab_devices;
+        if (slabs > 1) {
+            std::vector<int> given;
+            for (size_t p0 = 0; p0 < devlist.size();) {
+                const size_t p1 = devlist.find(',', p0);
+                given.push_back(std::atoi(devlist.substr(p0, p1 - p0).c_str()));
+                if (p1 == std::string::npos) break;
+                p0 = p1 + 1;
+            }
+            for (int r = 0; r < slabs; ++r) slab_devices.push_back(given.empty() ? device : given[r % given.size()]);
+        }
+        Backend gpu(n, fish_struc, seed, device, replicates, rolling, /*speed_norm = num*/ (double)n, 0, slab_devices);
         individuals fish;
         initialize(gpu, fish, n, 2, speed, fish_struc);                // :116
         std::vector<int> quality;
@@ -70,6 +86,7 @@ int main(int argc, char** argv) {
         std::vector<int32_t> intake;
         const bool logging = !log_q.empty() || !log_i.empty();
         const int rows = !log_i.empty() && intake_every > 0 ? (steps + intake_every - 1) / intake_every : 0;
+        if (unfused && gpu.slabs() > 1) throw Error(FISHABM_E_ARG, "--unfused is for an unsplit school");
         if (unfused) {                                                 // the reference's literal loop, :126-131
             if (logging) sumq.assign((size_t)steps * replicates, 0);
             if (rows) intake.assign((size_t)rows * replicates * n, 0);
@@ -81,13 +98,22 @@ int main(int argc, char** argv) {
                 if (rows && z % intake_every == 0)
                     gpu.ck(fishabm_get_state(gpu.ctx(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, intake.data() + (size_t)(z / intake_every) * replicates * n));
             }
-        } else if (logging) {
+        } else if (logging && gpu.slabs() == 1) {
             if (!log_q.empty()) sumq.assign((size_t)steps * replicates, 0);
             if (rows) intake.assign((size_t)rows * replicates * n, 0);
             gpu.ck(fishabm_run_logged(gpu.ctx(), steps, sumq.empty() ? nullptr : sumq.data(), intake.empty() ? nullptr : intake.data(), intake_every));
+        } else if (logging) {  // split school: the loggers read the slabs' partial sums / owned fish after every step
+            if (!log_q.empty()) sumq.assign((size_t)steps, 0);
+            if (rows) intake.assign((size_t)rows * n, 0);
+            for (int z = 0; z < steps; ++z) {
+                step(gpu, 1);
+                if (!log_q.empty()) sumq[z] = sum_array(gpu);
+                if (rows && z % intake_every == 0)
+                    gpu.each([&](fishabm_ctx* c) { return fishabm_get_state(c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, intake.data() + (size_t)(z / intake_every) * n); });
+            }
         } else {
             step(gpu, steps);
-            gpu.ck(fishabm_flush(gpu.ctx()));
+            gpu.each([&](fishabm_ctx* c) { return fishabm_flush(c); });
         }
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 

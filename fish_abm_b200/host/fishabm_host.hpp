@@ -40,27 +40,35 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
-// One school (or `replicates` independent schools) resident on one GPU.
+// One school (or `replicates` independent schools) resident on one GPU -- or one school split into x-slabs, one
+// context per slab, on the GPUs listed in `slab_devices` (all in this process: the slabs are attached to each other's
+// inboxes directly, the peer-memory transport of include/fishabm.h).
 class Backend {
   public:
     Backend(int n, const Structure& s, uint64_t seed, int device = 0, int replicates = 1, bool rolling = true, double speed_norm = 0.0,
-            uint32_t replicate0 = 0);
+            uint32_t replicate0 = 0, const std::vector<int>& slab_devices = {});
     ~Backend();
     Backend(const Backend&) = delete;
     Backend& operator=(const Backend&) = delete;
 
     int n() const { return n_; }
     int replicates() const { return reps_; }
-    fishabm_ctx* ctx() { return ctx_; }
+    int slabs() const { return (int)ctxs_.size(); }
+    fishabm_ctx* ctx(int k = 0) { return ctxs_[k]; }
+    // apply f to every context; for a split school the per-fish outputs of the slabs fill disjoint entries of the same
+    // whole-school arrays, so most calls are simply repeated on every slab
+    template <class F> void each(F f) { for (fishabm_ctx* c : ctxs_) ck(f(c), c); }
+    void step(int nsteps);                               // all slabs: enqueue, then wait (they wait for each other on the device)
+    long long sum_quality();
 
     void push(const individuals& inds);                  // host -> device (one school)
     void pull(individuals& inds);                        // device -> host
     void set_quality(const std::vector<int>& q, int rows, int cols);
     void get_quality(std::vector<int>& q, int replicate = 0);
-    void ck(int rc) const;
+    void ck(int rc, fishabm_ctx* c = nullptr) const;
 
   private:
-    fishabm_ctx* ctx_ = nullptr;
+    std::vector<fishabm_ctx*> ctxs_;
     int n_, reps_;
     Structure s_;
 };

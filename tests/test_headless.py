@@ -63,3 +63,18 @@ def test_driver_ensemble_rows_have_the_shape_of_the_reference_data(tmp_path, q10
         E.set_quality(q100)
         sumq, _ = E.run_logged(200)
     assert np.array_equal(dq[:, 1:], sumq.T)
+
+
+@pytest.mark.gpu
+def test_driver_split_school_equals_the_unsplit_run(tmp_path, q100):
+    """--slabs K: K slab contexts in the driver's process attached through peer memory; every log must be identical"""
+    outs = []
+    for k, extra in enumerate([[], ["--slabs", 2], ["--slabs", 4, "--devices", "0,0,0,0"]]):
+        lq, li = tmp_path / f"q{k}.csv", tmp_path / f"i{k}.csv"
+        r = run("--n", 3000, "--w", 2000, "--h", 2000, "--steps", 60, "--seed", 21, "--speed", 10, "--quality", QCSV, "--log-quality", lq,
+                "--log-intake", li, "--quiet", *extra)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((np.loadtxt(lq, delimiter=",", dtype=np.int64), np.loadtxt(li, delimiter=",", dtype=np.int64)))
+    for q, i in outs[1:]:
+        assert np.array_equal(q, outs[0][0]) and np.array_equal(i, outs[0][1])
+    assert outs[0][0][0] == 3499 and outs[0][0][-1] < 3499
