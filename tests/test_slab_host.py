@@ -60,6 +60,9 @@ def _bootstrap_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     uid = broadcast_unique_id(dist, rank)
+    from fish_abm_b200.slab import gather_endpoints
+    eps = gather_endpoints(dist, bytes([rank + 1]) * 96)   # the 96-byte inbox endpoints travel the same way
+    assert eps == [bytes([1]) * 96, bytes([2]) * 96]
     q.put((rank, uid))
     dist.barrier()
     dist.destroy_process_group()
