@@ -61,7 +61,7 @@ struct fishabm_ctx {
     size_t msg_stride = 0, inbox_bytes = 0;
     unsigned char *peer_left = nullptr, *peer_right = nullptr;
     void* ipc_opened[2] = {nullptr, nullptr};
-    bool p2p = false;
+    bool p2p = false, published = false;
     int seq = 0;                 // exchanges completed (the same on every rank)
     SlabHeader* ctr = nullptr;   // [2] local slot counters while packing into remote inboxes
     long long timeout_ns = 10000000000LL;
@@ -277,6 +277,21 @@ int open_out_messages(fishabm_ctx* ctx, SlabMsg* out_left, SlabMsg* out_right) {
     return 0;
 }
 
+// peer-memory transport: complete the two remote messages of exchange seq+1 (headers, then arrival flags)
+int publish(fishabm_ctx* ctx) {
+    const int s = ctx->seq + 1, slot = s & 1;
+    SlabPublishArgs pa{ctx->ctr + 0, ctx->ctr + 1,
+                       reinterpret_cast<SlabHeader*>(ctx->peer_left + inbox_msg_off(ctx, 1, slot)),
+                       reinterpret_cast<SlabHeader*>(ctx->peer_right + inbox_msg_off(ctx, 0, slot)),
+                       reinterpret_cast<int*>(ctx->peer_left + inbox_flag_off(ctx, 1, slot)),
+                       reinterpret_cast<int*>(ctx->peer_right + inbox_flag_off(ctx, 0, slot)), s};
+    slab_publish_kernel<<<1, 32, 0, ctx->stream>>>(pa);
+    ctx->launches += 1;
+    ctx->published = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // K5 (+ deferred food-grid writes); a move also packs the slab messages
 int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
     const Buffers& b = ctx->buf[ctx->cur];
@@ -293,6 +308,17 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.slab = ctx->slab ? 1 : 0;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
+    u.part = UPD_ALL;
+    if (ctx->slab && do_move && ctx->p2p && ctx->p.nranks > 1) {
+        // edges first: the two outermost owned columns per side hold every migrant and ghost; their messages are
+        // published while the interior is still being updated (the neighbours' arrive behind that work)
+        u.part = UPD_EDGES;
+        update_kernel<<<std::max(1, std::min(cdiv(ctx->cap, 256), cdiv(8 * ctx->cap_g, 256))), 256, 0, ctx->stream>>>(u);
+        int rc = publish(ctx);
+        if (rc) return rc;
+        u.part = UPD_MIDDLE;
+        ctx->launches += 1;
+    }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
     if (do_sample) {
@@ -321,16 +347,12 @@ int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_righ
 int exchange(fishabm_ctx* ctx, unsigned char** in_left, unsigned char** in_right) {
     if (ctx->p.nranks == 1) { *in_left = ctx->out_right; *in_right = ctx->out_left; return 0; }
     if (ctx->p2p) {
+        if (!ctx->published) { int rc = publish(ctx); if (rc) return rc; }  // (move() published after its edge columns)
+        ctx->published = false;
         const int s = ++ctx->seq, slot = s & 1;
-        SlabPublishArgs pa{ctx->ctr + 0, ctx->ctr + 1,
-                           reinterpret_cast<SlabHeader*>(ctx->peer_left + inbox_msg_off(ctx, 1, slot)),
-                           reinterpret_cast<SlabHeader*>(ctx->peer_right + inbox_msg_off(ctx, 0, slot)),
-                           reinterpret_cast<int*>(ctx->peer_left + inbox_flag_off(ctx, 1, slot)),
-                           reinterpret_cast<int*>(ctx->peer_right + inbox_flag_off(ctx, 0, slot)), s};
-        slab_publish_kernel<<<1, 32, 0, ctx->stream>>>(pa);
         slab_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<int*>(ctx->inbox + inbox_flag_off(ctx, 0, slot)),
                                                     reinterpret_cast<int*>(ctx->inbox + inbox_flag_off(ctx, 1, slot)), s, ctx->timeout_ns, ctx->err);
-        ctx->launches += 2;
+        ctx->launches += 1;
         CK(cudaGetLastError());
         *in_left = ctx->inbox + inbox_msg_off(ctx, 0, slot);
         *in_right = ctx->inbox + inbox_msg_off(ctx, 1, slot);

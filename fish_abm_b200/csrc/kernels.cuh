@@ -570,7 +570,12 @@ struct UpdateArgs {
     float speed_norm_inv2;   // 2 / num (get_speed's normaliser, fish_mod.cpp:590)
     int slab;           // pack migrants / ghosts for the two neighbours
     SlabMsg out_left, out_right;
+    int part;           // UPD_ALL, or (slabs, peer-memory transport) UPD_EDGES first and UPD_MIDDLE after the publish
 };
+// A fish moves less than one cell per step, so only the two outermost owned columns on each side can produce
+// migrants or ghosts: updating them FIRST lets the messages leave (slab_publish_kernel) while the bulk of the slab is
+// still being updated, and the neighbours' messages arrive behind that work instead of being waited for.
+enum { UPD_ALL = 0, UPD_EDGES = 1, UPD_MIDDLE = 2 };
 
 constexpr int ERR_SLAB_OVERFLOW = 1;   // a slab message or the fish arrays overflowed their capacity
 constexpr int ERR_STEP_TOO_LONG = 2;   // a fish moved further than one neighbour cell in one step (slab mode)
@@ -607,13 +612,8 @@ __global__ void slab_wait_kernel(const int* flag_left, const int* flag_right, in
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.cell_start[a.g.ncell]) return;
-    if (i < a.cell_start[a.g.own_c0] || i >= a.cell_start[a.g.own_c1]) {  // ghost: rebuilt by every exchange
-        if (a.do_move) a.next_cell[i] = -1;
-        return;
-    }
+// the state transition of the owned fish at sorted index i
+__device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
     float4 c0 = a.cold0[i];
     int4 c1 = a.cold1[i];
     const int mycell = a.cell[i];
@@ -675,6 +675,34 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     }
     a.cold0[i] = c0;
     a.cold1[i] = c1;
+}
+
+__global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int total = a.cell_start[a.g.ncell];
+    const int b1 = a.cell_start[a.g.own_c0], e2 = a.cell_start[a.g.own_c1];
+    if (a.part == UPD_ALL) {  // one thread per held entry
+        if (tid >= total) return;
+        if (tid < b1 || tid >= e2) { if (a.do_move) a.next_cell[tid] = -1; return; }  // ghost: rebuilt by every exchange
+        update_fish(a, tid);
+        return;
+    }
+    // owned fish = [b1,e1) (first two columns) + [e1,b2) (middle) + [b2,e2) (last two columns), contiguous in sorted order
+    const int edge_c = min(a.g.own_c0 + 2 * a.g.ny, a.g.own_c1);
+    const int e1 = a.cell_start[edge_c];
+    const int b2 = a.cell_start[max(a.g.own_c1 - 2 * a.g.ny, edge_c)];
+    if (a.part == UPD_EDGES) {  // grid-stride over: left ghosts, right ghosts, first edge, last edge
+        const int nl = b1, nr = total - e2, n1 = e1 - b1, n2 = e2 - b2;
+        for (int t = tid; t < nl + nr + n1 + n2; t += nthreads) {
+            if (t < nl) { if (a.do_move) a.next_cell[t] = -1; }
+            else if (t < nl + nr) { if (a.do_move) a.next_cell[e2 + (t - nl)] = -1; }
+            else if (t < nl + nr + n1) update_fish(a, b1 + (t - nl - nr));
+            else update_fish(a, b2 + (t - nl - nr - n1));
+        }
+    } else {                    // UPD_MIDDLE: one thread per fish of the interior columns
+        const int i = e1 + tid;
+        if (i < b2) update_fish(a, i);
+    }
 }
 
 // the deferred food-grid writes of one sample(); also clears the OTHER update counter (the two alternate by step)
