@@ -309,7 +309,8 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
     u.part = UPD_ALL;
-    if (ctx->slab && do_move && ctx->p2p && ctx->p.nranks > 1) {
+    static const bool edges_first = !(getenv("FISHABM_EDGES_FIRST") && atoi(getenv("FISHABM_EDGES_FIRST")) == 0);
+    if (ctx->slab && do_move && ctx->p2p && ctx->p.nranks > 1 && edges_first) {
         // edges first: the two outermost owned columns per side hold every migrant and ghost; their messages are
         // published while the interior is still being updated (the neighbours' arrive behind that work)
         u.part = UPD_EDGES;
