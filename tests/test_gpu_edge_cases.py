@@ -1,0 +1,151 @@
+"""More parity cases through the C ABI: non-square worlds (the cell list is column-major: any nx/ny mix-up shows here),
+exotic raw headings, fully lagged schools (Q8), jumps of several cells in one step."""
+import numpy as np
+import pytest
+
+from fish_abm_b200 import Ensemble, School, synth
+from fish_abm_b200.slab import LocalSlabs
+from oracle.pyoracle import Oracle, State
+
+pytestmark = pytest.mark.gpu
+TOL_RAD, TOL_POS = 1e-5, 1e-4
+INT_FIELDS = ("lag", "sample_rate", "food_intake")
+
+
+def state_wh(n, w, h, seed, **kw):
+    d = synth.uniform_state(n, max(w, h), max(w, h), seed=seed, **kw)
+    d["coords"][:, 0] = (d["coords"][:, 0] * (w / max(w, h))).astype(np.float32)
+    d["coords"][:, 1] = (d["coords"][:, 1] * (h / max(w, h))).astype(np.float32)
+    np.clip(d["coords"][:, 0], 0, np.nextafter(np.float32(w), np.float32(0)), out=d["coords"][:, 0])
+    np.clip(d["coords"][:, 1], 0, np.nextafter(np.float32(h), np.float32(0)), out=d["coords"][:, 1])
+    return d
+
+
+def wrapped_err(a, b, w, h):
+    d = np.abs(a - b)
+    d[:, 0] = np.minimum(d[:, 0], w - d[:, 0])
+    d[:, 1] = np.minimum(d[:, 1], h - d[:, 1])
+    return d.max()
+
+
+def step_against_oracle(S, d, w, h, q, seed, steps):
+    O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, h, q.copy(), seed=seed)
+    for s in range(steps):
+        assert np.array_equal(S.zone_counts(), O.zone_counts()), s
+        so = O.social(step=s)
+        assert np.abs(np.deg2rad(S.social()[0] - so["turn"]))[so["n_ties"] == 0].max() < TOL_RAD
+        S.move(); O.move_sync(s)
+        g = S.get_state()
+        assert np.abs(np.deg2rad(g["dir"] - O.state.dir)).max() < TOL_RAD
+        assert wrapped_err(g["coords"], O.state.coords, w, h) < TOL_POS
+        O.state = State(**{k: v.copy() for k, v in g.items()})
+        S.sample(); O.sample(s)
+        g = S.get_state()
+        for f in INT_FIELDS:
+            assert np.array_equal(g[f], getattr(O.state, f)), (f, s)
+        assert np.array_equal(S.get_quality(), O.quality)
+
+
+@pytest.mark.parametrize("w,h", [(3000, 1400), (800, 4600), (600, 2000)])
+def test_non_square_world(q100, w, h):
+    n = 6000
+    d = state_wh(n, w, h, 61, speed=9.0)
+    q = synth.tile_quality(q100, w, h)
+    assert q.shape == (h // 20, w // 20)
+    with School(n=n, w=w, h=h, seed=70) as S:
+        S.set_state(**d)
+        S.set_quality(q)
+        g = S.get_state()
+        for k in d:
+            assert np.array_equal(g[k], d[k]), k
+        step_against_oracle(S, d, w, h, q, 70, 3)
+
+
+def test_non_square_world_slabs_and_ensemble_equal_whole_school(q100):
+    w, h, n, steps = 2800, 1000, 5000, 12
+    d = state_wh(n, w, h, 62, speed=11.0)
+    q = synth.tile_quality(q100, w, h)
+    with School(n=n, w=w, h=h, seed=71) as S:
+        S.set_state(**d); S.set_quality(q); S.step(steps)
+        g, qa = S.get_state(), S.get_quality()
+    with LocalSlabs(3, n=n, w=w, h=h, seed=71) as P:
+        P.set_state(**d); P.set_quality(q); P.step(steps)
+        gp = P.get_state()
+        for k in g:
+            assert np.array_equal(gp[k], g[k]), k
+        assert np.array_equal(P.get_quality(), qa)
+    n2 = 700
+    d2 = {k: v[:n2] for k, v in d.items()}
+    with School(n=n2, w=w, h=h, seed=72) as S, Ensemble(1, n=n2, w=w, h=h, seed=72) as E:
+        S.set_state(**d2); S.set_quality(q); S.step(steps)
+        E.set_state(**{k: v[None] for k, v in d2.items()}); E.set_quality(q); E.step(steps)
+        ge, gs = E.get_state(), S.get_state()
+        for k in gs:
+            assert np.array_equal(ge[k][0], gs[k]), k
+        assert np.array_equal(E.get_quality(0), S.get_quality())
+
+
+def test_exotic_raw_headings(q100):
+    """raw headings in (-290, 650): getangle subtracts the RAW heading and wraps once (fish_mod.cpp:454-459), so beyond
+    +-540 it returns a non-standard representative that is then multiplied by the weight"""
+    n, w = 5000, 2000
+    d = synth.uniform_state(n, w, w, seed=63, lagged_fraction=0.0)
+    rng = np.random.default_rng(5)
+    d["dir"] = rng.uniform(-290, 650, n).astype(np.float32).astype(np.float64)
+    d["dir"][:400] = rng.uniform(540, 650, 400).astype(np.float32).astype(np.float64)
+    with School(n=n, seed=73) as S:
+        S.set_state(**d)
+        S.set_quality(q100)
+        O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, q100.copy(), seed=73)
+        assert np.array_equal(S.zone_counts(), O.zone_counts())
+        so = O.social(step=0)
+        turn = S.social()[0]
+        ok = (so["n_ties"] == 0) & (so["knife"] == 0)
+        assert ok[:400].sum() > 300
+        assert np.abs(np.deg2rad(turn - so["turn"]))[ok].max() < TOL_RAD
+        # the non-standard representative really occurs: the turn of an exotic fish differs from the same fish's turn
+        # with its heading reduced by 360 (same geometry, standard representative)
+        d2 = {k: v.copy() for k, v in d.items()}
+        d2["dir"][:400] -= 360.0
+        S.set_state(**d2)
+        turn2 = S.social()[0]
+        assert np.abs(turn[:400] - turn2[:400]).max() > 1.0
+        assert np.abs(turn[400:] - turn2[400:])[np.abs(d["dir"][400:]) < 500].max() < 1e-3
+
+
+def test_fully_lagged_school_only_jitters(q100):
+    """lagged fish never translate or wrap; their heading accumulates the +-10 error; lag counts down"""
+    n, w = 3000, 2000
+    d = synth.uniform_state(n, w, w, seed=64)
+    d["lag"][:] = 7
+    with School(n=n, seed=74) as S:
+        S.set_state(**d)
+        S.set_quality(q100)
+        S.step(5)
+        g = S.get_state()
+        assert np.array_equal(g["coords"], d["coords"])
+        assert np.array_equal(g["lag"], np.full(n, 2))
+        assert np.array_equal(g["sample_rate"], d["sample_rate"]) and S.sum_array() == int(q100.sum())
+        jitter = g["dir"] - d["dir"]
+        assert np.allclose(jitter, np.round(jitter), atol=1e-3) and np.abs(jitter).max() <= 50 and np.abs(jitter).max() > 10
+        errs = sum(np.array([S.draw(1, s, i, -10, 10) for i in range(50)]) for s in range(5))
+        assert np.allclose(jitter[:50], errs, atol=1e-3)
+
+
+def test_jumps_of_several_cells(q100):
+    """speed 450 with speed_factor up to 3: a fish crosses up to 6 neighbour cells in one step (whole-school mode has no
+    limit; slabs refuse such speeds)"""
+    n, w = 4000, 4000
+    d = synth.uniform_state(n, w, w, seed=65, speed=450.0, lagged_fraction=0.0)
+    d["speed_factor"][:] = np.random.default_rng(6).choice([0.5, 1.0, 2.5], n)
+    q = synth.tile_quality(q100, w, w)
+    with School(n=n, w=w, h=w, seed=75) as S:
+        S.set_state(**d)
+        S.set_quality(q)
+        O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, q.copy(), seed=75)
+        S.move(); O.move_sync(0)
+        g = S.get_state()
+        # a step of up to 1125 units carries the fp32 heading error (<= 1e-5 rad allowed, ~1e-6 observed) that far
+        assert wrapped_err(g["coords"], O.state.coords, w, w) < TOL_POS + 1125 * 2.5e-6
+        assert np.abs(np.deg2rad(g["dir"] - O.state.dir)).max() < TOL_RAD
+        assert np.array_equal(S.zone_counts(), Oracle(State(**{k: v.copy() for k, v in g.items()}), w, w, q.copy(), seed=75).zone_counts())
