@@ -68,13 +68,14 @@ typedef struct fishabm_params {
                               w x h window with its own food grid.  Arrays then hold replicates*n entries,
                               replicate-major.  fishabm_in_zone (arbitrary fov/r) and fishabm_feed are not available
                               for ensembles; fishabm_step completes its last sample() inside the call. */
-    int32_t rolling;       /* 1 = get_speed active (the committed reference, fish_mod.cpp:173); 0 = speed_factor only
-                              changes through feed() (the "non-rolling" variant of data/norolling_*) */
+    int32_t rolling;       /* 1 = get_speed active (the committed reference, fish_mod.cpp:173); 0 = get_speed skipped:
+                              speed_factor only changes through feed().  (The code that produced the reference's
+                              data/norolling_* files is not in its repository; this switch does not reproduce them.) */
     uint64_t seed;         /* Philox key; draws are addressed by (seed, replicate, step, fish id, stream, k) */
     double speed_norm;     /* the macro `num` in get_speed (fish_mod.cpp:590); 0 = use n */
     /* slab decomposition of one school across GPUs (one context per rank); 1 rank = whole world */
     int32_t rank, nranks;
-    int32_t n_global;      /* fish in the whole school when nranks > 1 (0 = n) */
+    int32_t n_global;      /* reserved: 0 or n (n is always the size of the WHOLE school, on every rank) */
     int32_t capacity;      /* per-rank entry capacity (owned fish + ghosts + one step's arrivals) when slabs are used
                               (0 = automatic: 1.3 x the uniform-density expectation) */
     int32_t halo_capacity;    /* ghosts per slab message (0 = automatic: 2 x fish per cell column + 4096) */
