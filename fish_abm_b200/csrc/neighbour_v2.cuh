@@ -5,8 +5,8 @@
 //             lane copies candidates t = lane, lane+32, ... with a branch-free range lookup into the window (SoA x, y,
 //             cos, sin in the focal cell's frame).  The window is staged once per cell and reused by every focal
 //             group when the stencil fits it (<= 256 candidates).
-//   focal     the ACTIVE fish of the cell are compacted (ballot) into groups of up to 32, wherever they sit in the cell.
-//   filter    every lane tests its candidates (cached in registers, 8 chunks of 32) against one focal fish with a cheap,
+//   focal     the ACTIVE fish of the cell are compacted (ballot) into groups of up to 16, wherever they sit in the cell.
+//   filter    every lane tests its candidates (read from the window, chunks of 32) against one focal fish with a cheap,
 //             conservative, sqrt-free predicate (inside the r=200 disc and not clearly behind the 330 deg cone);
 //             survivors are compacted into a per-focal queue in shared memory with ballot/popc.
 //   process   the queue is consumed 32 entries at a time, one pair per lane, all lanes working for the SAME focal fish:
@@ -16,6 +16,8 @@
 // Lanes stay full regardless of how many fish of the cell are active, and the expensive per-pair math only runs on
 // (almost only) interacting pairs.  Sums are integers, hence independent of candidate order: results are bit-identical
 // to the first design (neighbour_kernel) and across any re-sorting or slab split of the fish.
+// 64 registers and 6 KB of shared memory per warp: 4 CTAs (32 warps) per SM.  Measured at the benchmark state: 16 warps/SM
+// 344 us, 24 warps/SM (candidates cached in 16 registers per lane, 80 registers) 279 us, 32 warps/SM (this form) 266 us.
 // (A half-warp-per-focal variant of process was measured 6 % slower at the benchmark density: queues of ~60 entries
 // fill two 32-wide rounds as well as four 16-wide ones, and the half-warp reductions cost twice the REDUX issue slots.)
 #pragma once
@@ -26,7 +28,7 @@ namespace fishk {
 constexpr int V2_WARPS = 8;
 constexpr int V2_THREADS = V2_WARPS * 32;
 constexpr int V2_WIN = 256;           // candidates per window batch
-constexpr int V2_FMAX = 32;           // focal fish per group
+constexpr int V2_FMAX = 16;           // focal fish per group
 constexpr float V2_FAR = 1.0e18f;     // padding coordinate: fails the disc test
 constexpr float V2_KCONE = 0.93301270189f + 2.5e-4f;   // cos^2(165 deg) + margin
 constexpr float V2_R2HI = (CELL_F + 2.5e-4f) * (CELL_F + 2.5e-4f);
@@ -46,7 +48,7 @@ struct V2WarpSmem {
 constexpr size_t V2_SMEM_BYTES = sizeof(V2WarpSmem) * V2_WARPS;
 
 template <bool STATS>
-__global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const NeighArgs a) {
+__global__ void __launch_bounds__(V2_THREADS, 4) neighbour_kernel_v2(const NeighArgs a) {
     extern __shared__ __align__(16) unsigned char v2_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -157,21 +159,13 @@ __global__ void __launch_bounds__(V2_THREADS, 3) neighbour_kernel_v2(const Neigh
             for (int b = 0; b < nbatch; ++b) {
                 const int fill = (staged == b) ? min(T - b * V2_WIN, V2_WIN) : stage(b);
                 const int nch = (fill + 31) >> 5;
-                float cxr[V2_WIN / 32], cyr[V2_WIN / 32];  // this lane's candidates (padding fails the disc test)
-#pragma unroll
-                for (int ch = 0; ch < V2_WIN / 32; ++ch) {
-                    const bool in = ch < nch;
-                    cxr[ch] = in ? S.wx[ch * 32 + lane] : V2_FAR;
-                    cyr[ch] = in ? S.wy[ch * 32 + lane] : V2_FAR;
-                }
                 for (int f = 0; f < nf; ++f) {
                     const float4 F = S.frec[f];  // broadcast
                     // ---- filter (all candidates, cheap, conservative)
                     int qn = 0;
-#pragma unroll
-                    for (int ch = 0; ch < V2_WIN / 32; ++ch) {
-                        if (ch < nch) {
-                            const float dx = cxr[ch] - F.x, dy = cyr[ch] - F.y;
+                    for (int ch = 0; ch < nch; ++ch) {
+                        {
+                            const float dx = S.wx[ch * 32 + lane] - F.x, dy = S.wy[ch * 32 + lane] - F.y;
                             const float d2 = fmaf(dx, dx, dy * dy);
                             const float dot = fmaf(F.z, dx, F.w * dy);
                             // inside the disc, and not clearly behind the cone: dot > -|cos165| d, written sqrt-free with the
