@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(ENS_THREADS) ensemble_kernel(const EnsembleArg
                                        (long long)__reduce_add_sync(FULL, P.ax1), (long long)__reduce_add_sync(FULL, P.ay1),
                                        (long long)__reduce_add_sync(FULL, P.ax2), (long long)__reduce_add_sync(FULL, P.ay2)};
             const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
-            const int c200 = cfar & 0xFFFF, cfr = cfar >> 16, c100 = cnear & 0xFFFF, c15 = cnear >> 16;
-            const int ties = __reduce_add_sync(FULL, P.ties);
+            const int4 cc = unpack_counts(cfar, cnear);
+            const int c15 = cc.x, c100 = cc.y, c200 = cc.z, cfr = cc.w, ties = unpack_ties(cfar);
             if (lane == 0) {
                 const FocalResult r = focal_result(a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,
                                                    c15, c100, c200, cfr, sums, ties);

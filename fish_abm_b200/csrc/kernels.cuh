@@ -240,9 +240,15 @@ __device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k
 // heading.  `raw(rx, ry, kcode)` yields the candidate's unshifted in-cell offset and its stencil code for the re-check;
 // `ids(my, nb)` yields the two fish ids for a tie draw.  Returns true when the pair was re-checked in fp64.
 // counts are packed two to a word (16 bits each: a lane sees at most 32 candidates per reduction, a warp 1024):
-//   c_far = n200 | front << 16,  c_near = n100 | n15 << 16
-struct PairAcc { int c_far, c_near, ties; int ax0, ay0, ax1, ay1, ax2, ay2; };
-__device__ __forceinline__ void pair_acc_clear(PairAcc& A) { A.c_far = A.c_near = A.ties = 0; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0; }
+//   c_far = n200 | front << 16 | ties << 27,  c_near = n100 | n15 << 16
+// (ties = tie-break draws consumed, a diagnostic kept modulo 32)
+struct PairAcc { int c_far, c_near; int ax0, ay0, ax1, ay1, ax2, ay2; };
+constexpr int PAIR_TIE_UNIT = 1 << 27;
+__device__ __forceinline__ void pair_acc_clear(PairAcc& A) { A.c_far = A.c_near = 0; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0; }
+__device__ __forceinline__ int4 unpack_counts(int c_far, int c_near) {  // n15, n100, n200, front
+    return make_int4(c_near >> 16, c_near & 0xFFFF, c_far & 0xFFFF, (c_far >> 16) & 0x7FF);
+}
+__device__ __forceinline__ int unpack_ties(int c_far) { return (int)((unsigned)c_far >> 27); }
 
 template <class Raw, class Ids>
 __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float fc, float fs, float fdir, bool exotic, float qx, float qy,
@@ -287,13 +293,13 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
                 uint32_t my, nb;
                 ids(my, nb);
                 t = (fishrng::draw(seed, replicate, step_move, my, STREAM_CHOICE, nb, 0, 1) ? PI_F : -PI_F);
-                A.ties++;
+                A.c_far += PAIR_TIE_UNIT;
             }
         } else if (al && tie180) {  // exactly opposite heading (fish_mod.cpp:460-462)
             uint32_t my, nb;
             ids(my, nb);
             t = (fishrng::draw(seed, replicate, step_move, my, STREAM_CHOICE, nb, 0, 1) ? PI_F : -PI_F);
-            A.ties++;
+            A.c_far += PAIR_TIE_UNIT;
         }
         const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
         const float kz = in15 ? 0.1f : 0.004f;

@@ -40,7 +40,7 @@ struct V2WarpSmem {
     float4 frec[V2_FMAX];
     float fdir[V2_FMAX];
     int fidx[V2_FMAX];
-    int fties[V2_FMAX];
+    int fties[V2_FMAX];                                // tie draws across window batches (diagnostic)
     int run_pre[12];                                       // exclusive prefix of the 9 stencil cells' counts (+ total)
     int run_start[12];                                     // first sorted index of each stencil cell
     unsigned char queue[V2_WIN];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(V2_THREADS, 4) neighbour_kernel_v2(const Neigh
 
             // lane f keeps focal fish f's reduced sums of the current batch in registers; shared-memory accumulators are
             // only touched when the stencil needs more than one window batch
-            int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, mfar = 0, mnear = 0, mties = 0;
+            int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, mfar = 0, mnear = 0;
             for (int b = 0; b < nbatch; ++b) {
                 const int fill = (staged == b) ? min(T - b * V2_WIN, V2_WIN) : stage(b);
                 const int nch = (fill + 31) >> 5;
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(V2_THREADS, 4) neighbour_kernel_v2(const Neigh
                     const float4 F = S.frec[f];  // broadcast
                     // ---- filter (all candidates, cheap, conservative)
                     int qn = 0;
+#pragma unroll 2
                     for (int ch = 0; ch < nch; ++ch) {
                         {
                             const float dx = S.wx[ch * 32 + lane] - F.x, dy = S.wy[ch * 32 + lane] - F.y;
@@ -209,22 +210,21 @@ __global__ void __launch_bounds__(V2_THREADS, 4) neighbour_kernel_v2(const Neigh
                     const int r2 = __reduce_add_sync(FULL, P.ax1), r3 = __reduce_add_sync(FULL, P.ay1);
                     const int r4 = __reduce_add_sync(FULL, P.ax2), r5 = __reduce_add_sync(FULL, P.ay2);
                     const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
-                    const int tsum = __any_sync(FULL, P.ties != 0) ? __reduce_add_sync(FULL, P.ties) : 0;
                     if (STATS) st_inter += (unsigned)(cfar & 0xFFFF);
-                    if (lane == f) { m0 = r0; m1 = r1; m2 = r2; m3 = r3; m4 = r4; m5 = r5; mfar = cfar; mnear = cnear; mties = tsum; }
+                    if (lane == f) { m0 = r0; m1 = r1; m2 = r2; m3 = r3; m4 = r4; m5 = r5; mfar = cfar; mnear = cnear; }
                 }
                 if (nbatch > 1 && lane < nf) {
-                    const int4 cc = make_int4(mnear >> 16, mnear & 0xFFFF, mfar & 0xFFFF, mfar >> 16);
+                    const int4 cc = unpack_counts(mfar, mnear);
                     if (b == 0) {
                         S.acc[lane][0] = m0; S.acc[lane][1] = m1; S.acc[lane][2] = m2; S.acc[lane][3] = m3; S.acc[lane][4] = m4; S.acc[lane][5] = m5;
                         S.cnt[lane] = cc;
-                        S.fties[lane] = mties;
+                        S.fties[lane] = unpack_ties(mfar);
                     } else {
                         S.acc[lane][0] += m0; S.acc[lane][1] += m1; S.acc[lane][2] += m2; S.acc[lane][3] += m3; S.acc[lane][4] += m4; S.acc[lane][5] += m5;
                         int4 o = S.cnt[lane];
                         o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
                         S.cnt[lane] = o;
-                        S.fties[lane] += mties;
+                        S.fties[lane] += unpack_ties(mfar);
                     }
                 }
             }
@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(V2_THREADS, 4) neighbour_kernel_v2(const Neigh
                     finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], S.fties[lane]);
                 } else {
                     const long long sums[6] = {m0, m1, m2, m3, m4, m5};
-                    finish_focal(a, idx, k1, F.x, F.y, mnear >> 16, mnear & 0xFFFF, mfar & 0xFFFF, mfar >> 16, sums, mties);
+                    const int4 cc = unpack_counts(mfar, mnear);
+                    finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, sums, unpack_ties(mfar));
                 }
             }
             __syncwarp();
