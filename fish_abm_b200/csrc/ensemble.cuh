@@ -39,7 +39,7 @@ __host__ __device__ inline size_t ensemble_smem_bytes(int n, int qcells) {
     return (size_t)n * (16 + 16 + 16 + 16 + 4 + 4 + 4 + 4) + (size_t)((qcells + 15) / 16) * 16 + 64;
 }
 
-__global__ void __launch_bounds__(ENS_THREADS) ensemble_kernel(const EnsembleArgs a) {
+__global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const EnsembleArgs a) {
     extern __shared__ __align__(16) unsigned char ens_smem[];
     const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xFFFFFFFFu;
