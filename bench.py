@@ -112,6 +112,9 @@ def reference_arm(args, rank: int, world: int):
     workload: the full per-fish work of move()+sample() for `k` focal fish on the full frozen state."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the CPU implementation on ALL host cores, and the
+    # oracle port is an OpenMP loop: set the thread count before libgomp initialises (nothing has loaded it yet)
+    os.environ["OMP_NUM_THREADS"] = str(min(os.cpu_count() or 1, 32))
     from fish_abm_b200 import synth
     from oracle.pyoracle import Oracle, RefLib, State
     # the same workload as our arm: C3 (1M fish) for one GPU, C4 (16.8M fish) for several.  The compiled reference has a
@@ -131,8 +134,10 @@ def reference_arm(args, rank: int, world: int):
         run = lambda: R.time_focal(ids, cores)
     else:
         O = Oracle(State(**d), w, w, None, seed=1)
+        used = O.time_focal(ids[:1])[1]   # threads OpenMP really gives us
+        cores = used
         run = lambda: O.time_focal(ids)[0]
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(min(args.warmup, 2)):
         run()
     secs = [run() for _ in range(args.steps)]
     tot = float(np.sum(secs))
