@@ -268,16 +268,23 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     const float near_r = fminf(fminf(fabsf(d - 15.f), fabsf(d - 100.f)), fabsf(d - 200.f));
     const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
     const bool unc = (near_r < BAND_R || near_c < tb) && live;
-    bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
+    // classification values: the fp32 distance / bearing cosine, or -- for a borderline pair -- stand-ins that make the
+    // comparisons below reproduce the literal fp64 predicates (only two floats cross the rare branch, and the five
+    // flags are computed once, as predicates, after it)
+    float d_cls = d, ca_cls = ca;
     if (unc) {
         float rx, ry; int kcode;
         raw(rx, ry, kcode);
         const unsigned bits = exact_pair_bits(fx, fy, fdir, rx, ry, kcode);
-        in15 = bits & 1u; in100 = bits & 2u; in200 = bits & 4u; vis = bits & 8u; front = bits & 16u;
+        d_cls = (bits & 1u) ? 1.f : (bits & 2u) ? 50.f : (bits & 4u) ? 150.f : 300.f;   // dist < 15 / < 100 / < 200 / not
+        ca_cls = !(bits & 8u) ? -1.f : (bits & 16u) ? 0.5f : -0.5f;                      // angle >= 165 / < 90 / in between
     }
+    const bool in15 = d_cls < 15.f, in100 = d_cls < 100.f, in200 = d_cls < 200.f, vis = ca_cls > COS165_F, front = ca_cls > 0.f;
     const bool inter = live && vis && in200;
     A.c_far += (inter ? 1 : 0) + ((live && front && in200) ? 0x10000 : 0);
-    A.c_near += inter ? ((in100 ? 1 : 0) + (in15 ? 0x10000 : 0)) : 0;
+    int near_inc = in100 ? 1 : 0;        // in15 implies in100 (also after the fp64 re-check: same distance): one select
+    near_inc = in15 ? 0x10001 : near_inc;  // chain instead of two independent conversions and an add
+    A.c_near += inter ? near_inc : 0;
     if (inter) {
         const bool al = in100 && !in15;
         const float cross = fmaf(fc, dy, -fs * dx);
