@@ -231,11 +231,13 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed && ctx->nb_events_used >= 4096) timed = false;  // per-launch timing covers the first 4096 passes of a call
     if (timed) {
         if (ctx->nb_events_used == (int)ctx->nb_events.size()) {
             cudaEvent_t x, y;
             CK(cudaEventCreate(&x)); CK(cudaEventCreate(&y));
-            ctx->nb_events.emplace_back(x, y);
+            try { ctx->nb_events.emplace_back(x, y); }
+            catch (...) { cudaEventDestroy(x); cudaEventDestroy(y); return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
         }
         e0 = ctx->nb_events[ctx->nb_events_used].first; e1 = ctx->nb_events[ctx->nb_events_used].second;
         ctx->nb_events_used++;
@@ -448,7 +450,8 @@ int fetch(fishabm_ctx* ctx, T* user, const T* dev, int count, int width) {
         CK(cudaMemcpyAsync(user, dev, (size_t)count * width * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
         return 0;
     }
-    ctx->h_tmp.resize((size_t)count * width * sizeof(T) + 1);
+    try { ctx->h_tmp.resize((size_t)count * width * sizeof(T) + 1); }   // nothing may throw across the C boundary
+    catch (...) { return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
     CK(cudaMemcpyAsync(ctx->h_tmp.data(), dev, (size_t)count * width * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const T* src = reinterpret_cast<const T*>(ctx->h_tmp.data());
@@ -458,7 +461,8 @@ int fetch(fishabm_ctx* ctx, T* user, const T* dev, int count, int width) {
 }
 int fetch_ids(fishabm_ctx* ctx, int count) {
     if (!ctx->slab) return 0;
-    ctx->h_ids.resize((size_t)count + 1);
+    try { ctx->h_ids.resize((size_t)count + 1); }
+    catch (...) { return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
     CK(cudaMemcpyAsync(ctx->h_ids.data(), ctx->st_ids, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -891,8 +895,10 @@ int fishabm_initialize(fishabm_ctx* ctx, double speed) {
     // initialize(), fish_mod.cpp:183-206.  Tiny and one-off: the state is composed on the host from the same
     // counter-based streams the device uses, then ingested like any other state.
     const size_t n = (size_t)ctx->n * ctx->R;
-    std::vector<double> coords(2 * n), dir(n), sp(n, speed), sf(n, 1.0);
-    std::vector<int32_t> z(n, 0);
+    std::vector<double> coords, dir, sp, sf;
+    std::vector<int32_t> z;
+    try { coords.resize(2 * n); dir.resize(n); sp.assign(n, speed); sf.assign(n, 1.0); z.assign(n, 0); }
+    catch (...) { return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
     for (int r = 0; r < ctx->R; ++r) {
         const uint32_t rep = ctx->p.replicate0 + (uint32_t)r;
         for (int f = 0; f < ctx->n; ++f) {

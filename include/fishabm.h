@@ -167,7 +167,8 @@ int fishabm_draw(const fishabm_ctx* ctx, int32_t stream, uint32_t replicate, uin
                  int32_t a, int32_t b, int32_t* out);
 /* device time of the most recent fishabm_move/sample/step call, CUDA events on the library's stream */
 int fishabm_last_step_ms(const fishabm_ctx* ctx, float* ms);
-/* device time of the neighbour kernel alone, summed over the most recent call, and its launch count */
+/* device time of the neighbour kernel alone, summed over the (first 4096) launches of the most recent call, and that
+ * launch count */
 int fishabm_last_neighbour_ms(const fishabm_ctx* ctx, float* ms, int32_t* launches);
 int fishabm_last_pass_stats(fishabm_ctx* ctx, fishabm_pass_stats* out);
 /* kernels launched by this context since creation (for the benchmark's gpu_launches) */
