@@ -49,7 +49,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -205,11 +205,11 @@ def ours(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput: K steps, each timed on the library's stream with CUDA events
+    clocks = ClockSampler(local_rank)   # sampled from the warm-up through the end of the timed steps
+    clocks.start()
     for _ in range(args.warmup):
         S.step(1)
     S.flush()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     launches0 = S.launch_count()
     torch.cuda.synchronize()
     step_ms, nb_ms, nb_launches = [], 0.0, 0

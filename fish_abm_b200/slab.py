@@ -242,12 +242,12 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
         dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)   # sampled from the warm-up through the end of the timed steps
+    clocks.start()
     for _ in range(args.warmup):
         S.step(1)
     S.flush()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     launches0 = S.launch_count()
     # K steps in one library call per rank: neighbour pass, update+pack, NCCL exchange, ingest, sort, all on the
     # library's stream with no host synchronisation in between; the trailing sample() is part of the K steps
