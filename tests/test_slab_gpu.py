@@ -149,6 +149,30 @@ def test_peer_memory_timeout_is_reported_not_hung(q100, monkeypatch):
         assert e.value.code == -5 and "did not arrive" in str(e.value)
 
 
+def test_slab_queries_and_feed_match_whole_school(q100):
+    """in_zone with arbitrary fov / r, get_speed and feed() through slab contexts (each serves the ids it owns)"""
+    n, w = 12_000, 2400
+    d = synth.uniform_state(n, w, w, seed=52)
+    q = synth.tile_quality(q100, w, w)
+    ids = np.random.default_rng(7).choice(n, 300, replace=False).astype(np.int32)
+    with School(n=n, w=w, h=w, seed=81) as S:
+        S.set_state(**d); S.set_quality(q)
+        want_zone, want_speed = S.in_zone(200, 150.0), S.get_speed()
+        S.feed(ids)
+        want_state, want_q = S.get_state(), S.get_quality()
+    with LocalSlabs(3, n=n, w=w, h=w, seed=81) as P:
+        P.set_state(**d); P.set_quality(q)
+        assert np.array_equal(P.in_zone(200, 150.0), want_zone)
+        from fish_abm_b200.slab import merge_owned
+        assert np.array_equal(merge_owned([s.get_speed() for s in P.S], float("nan")), want_speed)
+        for s in P.S:
+            s.feed(ids)   # every slab is given the whole list and feeds the fish it owns, in list order
+        got = P.get_state()
+        for k in FIELDS:
+            assert np.array_equal(got[k], want_state[k]), k
+        assert np.array_equal(P.get_quality(), want_q)
+
+
 def test_one_column_slabs_are_rejected(q100):
     """a slab needs two owned columns (a migrant into a one-column slab would also be a ghost for the slab beyond)"""
     from fish_abm_b200 import FishAbmError
