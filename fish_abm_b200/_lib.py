@@ -50,7 +50,7 @@ SYMBOLS = [
     "fishabm_slab_get_info", "fishabm_slab_unique_id", "fishabm_slab_connect", "fishabm_slab_begin_step",
     "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy", "fishabm_slab_get_endpoint",
     "fishabm_slab_attach", "fishabm_step_enqueue", "fishabm_wait", "fishabm_set_state_owned", "fishabm_get_state_owned",
-    "fishabm_create_environment",
+    "fishabm_create_environment", "fishabm_check_fp64",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -114,6 +114,7 @@ def load():
     L.fishabm_slab_attach.argtypes = [vp, C.POINTER(SlabEndpoint), C.POINTER(SlabEndpoint)]
     L.fishabm_step_enqueue.argtypes = [vp, i32]
     L.fishabm_wait.argtypes = [vp]
+    L.fishabm_check_fp64.argtypes = [vp, vp, i32, vp, vp, vp]
     L.fishabm_create_environment.argtypes = [C.c_uint64, u32, i32, vp, i32, i32, i32]
     L.fishabm_set_state_owned.argtypes = [vp, i32] + [vp] * 8
     L.fishabm_get_state_owned.argtypes = [vp, C.POINTER(i32)] + [vp] * 8

@@ -183,7 +183,7 @@ cudaError_t preload_kernels() {
     L((const void*)neighbour_kernel_v2<false>); L((const void*)neighbour_kernel_v2<true>); L((const void*)scan_finish_kernel);
     L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
     L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
-    L((const void*)sum_quality_kernel); L((const void*)update_kernel);
+    L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel);
     return e;
 }
 
@@ -1107,6 +1107,32 @@ int fishabm_in_zone(fishabm_ctx* ctx, int32_t fov_deg, double r, int32_t* out) {
     if ((rc = fetch_ids(ctx, cnt))) return rc;
     if ((rc = fetch(ctx, out, ctx->st_lag, cnt, 1))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fishabm_check_fp64(fishabm_ctx* ctx, const int32_t* ids, int32_t k, int32_t* counts4, double* turn, int32_t* flags) {
+    int rc = need_state(ctx);
+    if (rc) return rc;
+    if (!ids || k < 0 || !counts4 || !turn || !flags) return fail(ctx, FISHABM_E_ARG, "fishabm_check_fp64: null argument");
+    if (ctx->slab || ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_check_fp64 needs a whole-school context (every fish on this device)");
+    if (k > ctx->n) return fail(ctx, FISHABM_E_ARG, "fishabm_check_fp64: at most n ids per call");
+    if (k == 0) return 0;
+    CK(cudaSetDevice(ctx->p.device));
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    const Buffers& b = ctx->buf[ctx->cur];
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->st_ids, ids, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->pos_of_id, 0xFF, (size_t)ctx->n * sizeof(int), s));
+    index_by_id_kernel<<<cdiv(ctx->cap, 256), 256, 0, s>>>(b.cold1, ctx->cell_start, ctx->g, ctx->pos_of_id);
+    CheckArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->pos_of_id, ctx->st_ids, k, ctx->st_i4, ctx->st_dir, ctx->st_lag,
+                ctx->n, ctx->g, ctx->p.w, ctx->p.h, ctx->step, ctx->p.seed, ctx->p.replicate0};
+    check_fp64_kernel<<<cdiv(k * 32, 256), 256, 0, s>>>(a);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts4, ctx->st_i4, (size_t)k * 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(turn, ctx->st_dir, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(flags, ctx->st_lag, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return 0;
 }
 

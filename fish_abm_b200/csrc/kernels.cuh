@@ -1070,6 +1070,131 @@ __global__ void in_zone_generic_kernel(const ZoneArgs a) {
     if (a.ids) a.ids[pos] = id;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// fp64 check mode (FISHABM_MODE_BRUTE_FP64's evaluator, fishabm_check_fp64): in_zone counts and the social() turn of
+// listed fish by brute force over ALL fish of the school, in double precision, restating the reference's own formulas
+// (in_zone fish_mod.cpp:226-260, social :262-377, averageturn :379-408, getangle :420-464) -- nothing shared with the
+// product path: no cell list, no fp32 pair math, no polynomial atan2, no fixed-point sums.  One warp per listed fish,
+// candidates across the lanes (so sums are reduced in a different order than the reference's id order: ~1e-13 deg).
+// ------------------------------------------------------------------------------------------------------
+struct CheckArgs {
+    const float4* rec; const float4* cold0; const int4* cold1; const int* cell; const int* pos_of_id;
+    const int* ids; int k;
+    int* counts4; double* turn; int* flags;
+    int n; Grid g; int w, h;
+    uint32_t step; uint64_t seed; uint32_t replicate;
+};
+enum { CHECK_RANDOMWALK = 1, CHECK_TIES = 2, CHECK_KNIFE = 4 };
+
+__device__ __forceinline__ double check_fold(double d, int extent) {  // :239-250: int halves, strict compares
+    if (d > extent / 2) return d - extent;
+    if (d < -extent / 2) return d + extent;
+    return d;
+}
+// getangle (:420-464) for an offset (x,y) already folded; *tie: the reference would draw distrib_choice (:460-462)
+__device__ __forceinline__ double check_getangle(double x, double y, double fdir, bool* tie) {
+    double angle = acos(x / sqrt(x * x + y * y)) * 180.0 / M_PI;
+    if (y < 0) angle = 360.0 - angle;
+    else if (y == 0) angle = (x >= 0) ? 0.0 : 180.0;
+    angle = angle - fdir;
+    if (angle < 0) angle += 360.0; else if (angle >= 360.0) angle -= 360.0;  // correctangle, once
+    *tie = false;
+    if (angle > 180.0) angle -= 360.0;
+    else if (angle == 180.0) *tie = true;
+    return angle;
+}
+__device__ __forceinline__ double check_averageturn(double xs, double ys, int count) {  // :379-408 from the cos/sin sums
+    const double x = xs / count, y = ys / count;
+    double angle = acos(x / sqrt(x * x + y * y)) * 180.0 / M_PI;
+    if (y < 0) angle = -angle;
+    else if (y == 0) angle = (x >= 0) ? 0.0 : 180.0;
+    return angle;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.k) return;
+    const int id = a.ids[warp];
+    const int fi = (id >= 0 && id < a.n) ? a.pos_of_id[id] : -1;
+    if (fi < 0) { if (lane == 0) { a.turn[warp] = nan(""); a.flags[warp] = -1; for (int q = 0; q < 4; ++q) a.counts4[4 * warp + q] = -1; } return; }
+    const int ny = a.g.ny;
+    auto world = [&](int i, double& X, double& Y) {  // exact: cell * 200 + fp32 offset
+        const float4 r = a.rec[i];
+        const int c = a.cell[i];
+        X = (double)((a.g.gx0 + c / ny) % a.g.nx_g) * 200.0 + (double)r.x;
+        Y = (double)(c % ny) * 200.0 + (double)r.y;
+    };
+    double fx, fy;
+    world(fi, fx, fy);
+    const double fdir = (double)a.cold0[fi].x;
+    const double dx0 = cos(fdir * M_PI / 180.0), dy0 = sin(fdir * M_PI / 180.0);
+    int c15 = 0, c100 = 0, c200 = 0, cf = 0, ties = 0, knife = 0;
+    double avx = 0, avy = 0, alx = 0, aly = 0, atx = 0, aty = 0;
+    for (int j = lane; j < a.n; j += 32) {
+        if (j == fi) continue;
+        double X, Y;
+        world(j, X, Y);
+        const double x = check_fold(X - fx, a.w), y = check_fold(Y - fy, a.h);
+        if (!(x * x + y * y < 40000.5)) continue;  // nothing below can hold beyond r = 200
+        const double dist = sqrt(x * x + y * y);
+        const double angle = acos((dx0 * x + dy0 * y) / dist) * 180.0 / M_PI;  // NaN (coincident / rounding) fails every test
+        if (angle < 90.0 && dist < 200.0) cf++;                                 // get_speed's in_zone(180, 200), :589
+        if (!(angle < 165.0 && dist < 200.0)) continue;                         // :254, :315 (fov/2 = 165)
+        c200++; if (dist < 100.0) c100++; if (dist < 15.0) c15++;
+        const uint32_t nid = (uint32_t)a.cold1[j].w;
+        bool tie;
+        double t;
+        if (dist < 15.0) {            // avoid, :316-332
+            double b = check_getangle(x, y, fdir, &tie);
+            if (tie) { b = (fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_CHOICE, nid, 0, 1) - 0.5) * 360.0; ties++; }
+            if (fabs(b) < 1e-4 || fabs(fabs(b) - 180.0) < 1e-4) knife++;
+            if (b > 0) t = b - 180.0;
+            else if (b < 0) t = b + 180.0;
+            else { t = b + (fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_CHOICE, nid, 0, 1) - 0.5) * 360.0; ties++; }
+            t = t * (1.0 / (0.1 * (dist * dist) + 2.0));
+            avx += cos(t * M_PI / 180.0); avy += sin(t * M_PI / 180.0);
+        } else if (dist < 100.0) {    // align, :333-344: the neighbour's heading vector added to the focal position
+            const double jd = (double)a.cold0[j].x;
+            const double px = cos(jd * M_PI / 180.0) + fx, py = sin(jd * M_PI / 180.0) + fy;
+            double b = check_getangle(check_fold(px - fx, a.w), check_fold(py - fy, a.h), fdir, &tie);
+            if (tie) { b = (fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_CHOICE, nid, 0, 1) - 0.5) * 360.0; ties++; }
+            if (fabs(fabs(b) - 180.0) < 1e-4) knife++;
+            t = b * (1.0 / (0.004 * ((dist - 15.0) * (dist - 15.0)) + 2.0));
+            alx += cos(t * M_PI / 180.0); aly += sin(t * M_PI / 180.0);
+        } else {                      // attract, :345-351
+            double b = check_getangle(x, y, fdir, &tie);
+            if (tie) { b = (fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_CHOICE, nid, 0, 1) - 0.5) * 360.0; ties++; }
+            if (fabs(fabs(b) - 180.0) < 1e-4) knife++;
+            t = b * (1.0 / (0.004 * ((dist - 200.0) * (dist - 200.0)) + 2.0));
+            atx += cos(t * M_PI / 180.0); aty += sin(t * M_PI / 180.0);
+        }
+    }
+    c15 = __reduce_add_sync(0xFFFFFFFFu, c15); c100 = __reduce_add_sync(0xFFFFFFFFu, c100);
+    c200 = __reduce_add_sync(0xFFFFFFFFu, c200); cf = __reduce_add_sync(0xFFFFFFFFu, cf);
+    ties = __reduce_add_sync(0xFFFFFFFFu, ties); knife = __reduce_add_sync(0xFFFFFFFFu, knife);
+    avx = warp_sum(avx); avy = warp_sum(avy); alx = warp_sum(alx); aly = warp_sum(aly); atx = warp_sum(atx); aty = warp_sum(aty);
+    if (lane != 0) return;
+    const int n_av = c15, n_al = c100 - c15, n_at = c200 - c100;
+    double turn;
+    int fl = (ties ? CHECK_TIES : 0) | (knife ? CHECK_KNIFE : 0);
+    if (n_av > 0) turn = check_averageturn(avx, avy, n_av);             // :356-358
+    else if (n_al > 0 && n_at > 0) {                                    // :360-365: weights 1.7 / 0.7
+        const double A = check_averageturn(alx, aly, n_al), T = check_averageturn(atx, aty, n_at);
+        const double xs = cos(A * M_PI / 180.0) * 1.7 + cos(T * M_PI / 180.0) * 0.7;
+        const double ys = sin(A * M_PI / 180.0) * 1.7 + sin(T * M_PI / 180.0) * 0.7;
+        turn = check_averageturn(xs, ys, 2);
+    } else if (n_al > 0) turn = check_averageturn(alx, aly, n_al);
+    else if (n_at > 0) turn = check_averageturn(atx, aty, n_at);
+    else { turn = (double)fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_RANDOMWALK, 0, -45, 45); fl |= CHECK_RANDOMWALK; }  // :372-374
+    a.counts4[4 * warp] = c15; a.counts4[4 * warp + 1] = c100; a.counts4[4 * warp + 2] = c200; a.counts4[4 * warp + 3] = cf;
+    a.turn[warp] = turn;
+    a.flags[warp] = fl;
+}
+
 __global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long long* out) {
     unsigned long long s = 0;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) s += q[k];

@@ -177,6 +177,15 @@ class School:
         self._ck(self.L.fishabm_social(self.ctx, _p(turn), _p(na), _p(nl), _p(nt)))
         return turn, na, nl, nt
 
+    def check_fp64(self, ids):
+        """fp64 check mode: (counts [k,4], turn [k], flags [k]) of the listed fish by brute force over the whole school in
+        double precision (include/fishabm.h: fishabm_check_fp64)"""
+        ids = np.ascontiguousarray(ids, np.int32)
+        k = len(ids)
+        counts, turn, flags = np.empty((k, 4), np.int32), np.empty(k), np.empty(k, np.int32)
+        self._ck(self.L.fishabm_check_fp64(self.ctx, _p(ids), k, _p(counts), _p(turn), _p(flags)))
+        return counts, turn, flags
+
     def get_speed(self) -> np.ndarray:
         out = np.full(self.total, np.nan)
         self._ck(self.L.fishabm_get_speed(self.ctx, _p(out)))

@@ -44,7 +44,7 @@ enum {
 enum {
     FISHABM_MODE_CELL_FP32 = 0,  /* product path: cell list + fused fp32 neighbour kernel with fp64 re-check
                                     of borderline predicates */
-    FISHABM_MODE_BRUTE_FP64 = 1, /* check mode: all-pairs, fp64, candidate order = id order, literal restatement (not built) */
+    FISHABM_MODE_BRUTE_FP64 = 1, /* not a context mode: the fp64 brute-force evaluator is the call fishabm_check_fp64 */
     FISHABM_MODE_ENSEMBLE = 2    /* replicate ensemble: one CTA per school, all pairs in shared memory; implied by
                                     replicates > 1, may be forced for a single school (n <= 1024) */
 };
@@ -137,6 +137,14 @@ int fishabm_zone_counts(fishabm_ctx* ctx, int32_t* out4);
 int fishabm_social(fishabm_ctx* ctx, double* turn, int32_t* n_avoid, int32_t* n_align, int32_t* n_attract);
 /* get_speed's value 1 + 2*in_zone(180,200)/num for every id, fish_mod.cpp:588-591, without storing it */
 int fishabm_get_speed(fishabm_ctx* ctx, double* out);
+
+/* fp64 check mode: the four in_zone counts and the social() turn of the k listed fish, by brute force over ALL fish
+ * of the school in double precision, restating fish_mod.cpp:226-260, 262-377, 379-464 literally -- independent of the
+ * cell list, of the fp32 pair arithmetic and of the fixed-point sums the product path uses (sums are reduced in a
+ * different order than the reference's id order: agreement with a CPU evaluation is ~1e-12 deg, not bitwise).
+ * flags[i]: bit 0 random walk, bit 1 tie-break draws consumed, bit 2 a bearing within 1e-4 deg of a discontinuity of
+ * the turn rule (the reference's own answer then hinges on rounding noise).  Whole-school contexts only; O(k * n). */
+int fishabm_check_fp64(fishabm_ctx* ctx, const int32_t* ids, int32_t k, int32_t* counts4, double* turn, int32_t* flags);
 
 /* ---- stepping ------------------------------------------------------------------------------------------ */
 /* move(inds,struc), fish_mod.cpp:163-181, synchronous form (every fish reads the pre-call state) */
