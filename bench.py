@@ -301,6 +301,17 @@ def ours(args, rank: int, world: int, local_rank: int):
     e2e = {"value": n * e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h2d + 8),
            "steps": e2e_steps, "api": "fishabm_set_state + fishabm_step(1) + fishabm_get_state + fishabm_sum_quality, pinned host buffers"}
 
+    # ---- live parity figure at the benchmark size: the state the timed run ended in, 1024 fish against ALL others in the
+    # library's fp64 check mode (brute force, double precision, the reference's formulas; pinned against the CPU oracle by
+    # tests/test_check_fp64_gpu.py)
+    cid = np.random.default_rng(9).choice(n, 1024, replace=False).astype(np.int32)
+    cc, ct, cf = S.check_fp64(cid)
+    zc, st = S.zone_counts()[cid], S.social()[0][cid]
+    okc = (cf & 6) == 0
+    parity = {"checked_fish": int(len(cid)), "against": "fishabm_check_fp64 (fp64 brute force over all fish)",
+              "count_mismatches": int((zc != cc).any(axis=1).sum()),
+              "max_turn_err_rad": float(np.abs(np.deg2rad(st - ct))[okc].max()), "knife_edge_or_tie_skipped": int((~okc).sum())}
+
     cpu = cpu_baseline_leg(n, w, d) if not args.no_cpu_baseline else None
     S.close()
     line = {"metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": args.steps,
@@ -311,7 +322,7 @@ def ours(args, rank: int, world: int, local_rank: int):
                        "l2": "flushed between steps (256 MiB write)" if flush is not None else "state larger than L2",
                        "timing": "CUDA events on the library's stream around each fishabm_step(1); K steps + the trailing sample pass"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "parity_spot_check": parity}
     print(json.dumps(line), flush=True)
 
 
