@@ -263,8 +263,9 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     const float d = d2 * rinv;
     const float dot = fmaf(fc, dx, fs * dy);
     const float ca = dot * rinv;
-    // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
-    const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
+    // rounding bands: position quantisation (<= 3e-5 units) dominates at short range; the constant covers the fp32
+    // heading unit vector (<= 5e-7), MUFU.RSQ (2.4e-7) and the dot product's rounding with a factor of two to spare
+    const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
     const float near_r = fminf(fminf(fabsf(d - 15.f), fabsf(d - 100.f)), fabsf(d - 200.f));
     const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
     const bool unc = (near_r < BAND_R || near_c < tb) && live;
@@ -325,6 +326,8 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
 
 // heading unit vector of a stored heading (degrees, fp32): THE one place it is computed, so that a state that went
 // through get_state / set_state continues bit-identically to one that stayed on the device
+// (a true division: multiplying by a rounded 1/180 would triple the error of the unit vector, which the bearing bands of
+// pair_math budget for)
 __device__ __forceinline__ void heading_vector(float dir_deg, float& cs, float& sn) { sincospif(dir_deg / 180.f, &sn, &cs); }
 
 // move() for one fish (fish_mod.cpp:165-179) in cell/offset form.  In: record, cold state, cell (cx,cy), social turn,
@@ -346,8 +349,10 @@ __device__ __forceinline__ void move_core(float4& r, float4& c0, int lag, int& c
         const float px = fmaf(stepl, cs, r.x), py = fmaf(stepl, sn, r.y);
         if (rolling) c0.z = fmaf((float)front, speed_norm_inv2, 1.0f);  // get_speed: 1 + 2*count/num, :588-591
         // periodic wrap (correct_coords, :466-480) in cell/offset form
-        const float kx = floorf(px / CELL_F), ky = floorf(py / CELL_F);
-        float ox = px - kx * CELL_F, oy = py - ky * CELL_F;
+        // (multiplying by 1/200 may misplace a value within an ulp of a cell edge by one cell: the two fix-ups below
+        // bring the offset back into [0, 200) either way)
+        const float kx = floorf(px * (1.f / CELL_F)), ky = floorf(py * (1.f / CELL_F));
+        float ox = fmaf(-kx, CELL_F, px), oy = fmaf(-ky, CELL_F, py);
         cx += (int)kx; cy += (int)ky;
         if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
         if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
@@ -379,7 +384,7 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         const float dot = fmaf(fc, dx, fs * dy);
         const float ca = dot * rinv;  // cos of the bearing of j seen from i
         // rounding bands: position quantisation (<= 3e-5 units) dominates at short range
-        const float tb = fmaf(rinv, 1.0e-4f, 1.0e-6f);
+        const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
         bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
         unc = unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb;
         bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
