@@ -148,6 +148,8 @@ def reference_arm(args, rank: int, world: int):
         used = O.time_focal(ids[:1])[1]   # threads OpenMP really gives us
         cores = used
         run = lambda: O.time_focal(ids)[0]
+    if n > N_C3:   # a C4-sized step is ~5-7 s of all-core work: keep the whole arm to about a minute and a half
+        args.steps, args.warmup = min(args.steps, 8), min(args.warmup, 1)
     for _ in range(min(args.warmup, 2)):
         run()
     secs = [run() for _ in range(args.steps)]
