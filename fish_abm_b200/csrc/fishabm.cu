@@ -608,6 +608,14 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     bool ok = true;
     auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; g_create_error = cudaGetErrorString(r); } };
     A(preload_kernels());
+    {   // the host libm's unit vectors of integer headings (kernels.cuh: g_unit_deg), written exactly as fish_mod.cpp:232-233
+        static double2 tab[UNIT_DEG_MAX - UNIT_DEG_MIN + 1];
+        for (int d = UNIT_DEG_MIN; d <= UNIT_DEG_MAX; ++d) {
+            volatile double dir = (double)d;  // no constant folding: the run-time libm is the reference's
+            tab[d - UNIT_DEG_MIN] = make_double2(cos(dir * M_PI / 180), sin(dir * M_PI / 180));
+        }
+        A(cudaMemcpyToSymbol(g_unit_deg, tab, sizeof tab));
+    }
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
     for (int k = 0; k < (ens ? 1 : 2) && ok; ++k) {
@@ -764,8 +772,11 @@ int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids,
     CK(cudaSetDevice(ctx->p.device));
     if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     ctx->pending_sample = false;
-    for (int i = 0; i < count; ++i)
+    for (int i = 0; i < count; ++i) {
         if (!(speed[i] * 3.0 < (double)CELL_I)) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: speed %g: slabs need 3*speed < 200", speed[i]);
+        // ids index pos_of_id[] on the device and the caller's arrays in fetch(): reject anything outside the school here
+        if (ids[i] < 0 || ids[i] >= ctx->n) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: ids[%d] = %d is outside [0, %d)", i, ids[i], ctx->n);
+    }
     const size_t n = (size_t)count;
     cudaStream_t s = ctx->stream;
     { int rcb = begin_timed(ctx); if (rcb) return rcb; }
@@ -1430,6 +1441,13 @@ int fishabm_get_step(const fishabm_ctx* ctx, uint32_t* step) {
 }
 int fishabm_set_step(fishabm_ctx* ctx, uint32_t step) {
     if (!ctx) return FISHABM_E_ARG;
+    if (ctx->step_open) return fail(ctx, FISHABM_E_STATE, "a slab step is open: call fishabm_slab_end_step first");
+    // a pending sample() belongs to the OLD step index (its draws are keyed by it): complete it before renumbering
+    if (ctx->have_state && ctx->pending_sample) {
+        CK(cudaSetDevice(ctx->p.device));
+        int rc = flush_pending(ctx);
+        if (rc) return rc;
+    }
     ctx->step = step;
     return 0;
 }

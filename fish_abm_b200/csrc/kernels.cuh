@@ -46,6 +46,7 @@ constexpr int NB_CAP = 256;              // candidate records staged per warp ba
 constexpr float PI_F = 3.14159265358979f;
 constexpr float COS165_F = -0.96592582628906829f;   // cos(165 deg): the 330 deg field of view (fov/2, fish_mod.cpp:254)
 constexpr float BAND_R = 2.0e-4f;        // |d - r| below this -> fp64 re-check
+constexpr float COLLINEAR_BAND = 1.0e-6f; // |sin(bearing)| below this, neighbour ahead -> fp64 re-check (acos(q > 1) = NaN drop)
 constexpr int FIX_SHIFT = 20;            // fixed-point fraction bits of the cos/sin accumulators
 constexpr float FIX_MAGIC = 12.0f;       // x + 12.0f has ulp 2^-20 for x in [-1,1]
 constexpr int FIX_MAGIC_BITS = 0x41400000;
@@ -113,6 +114,25 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     return copysignf(r, y);
 }
 
+// cos / sin of every INTEGER heading in [-720, 1080] degrees as the HOST's libm (glibc, the reference's own libm)
+// evaluates cos(dir * M_PI / 180) / sin(...) (fish_mod.cpp:232-233), uploaded once per device by fishabm_create.  CUDA's
+// fp64 cos/sin may differ from glibc's in the last ulp; on integer-lattice states with integer headings -- the reference's
+// own initial state, fish_mod.cpp:196-202 -- exactly collinear neighbours make the reference's `acos(q)` flip between a
+// number and NaN on that ulp, so the literal fp64 predicates below take the unit vector from this table
+// whenever the heading is an integer; any other heading uses the device's cos/sin (no exact collinearity to decide).
+constexpr int UNIT_DEG_MIN = -720, UNIT_DEG_MAX = 1080;
+__device__ double2 g_unit_deg[UNIT_DEG_MAX - UNIT_DEG_MIN + 1];
+__device__ __forceinline__ void unit_vector_fp64(float dir_deg, double& c, double& s) {
+    const float r = rintf(dir_deg);
+    if (r == dir_deg && r >= (float)UNIT_DEG_MIN && r <= (float)UNIT_DEG_MAX) {
+        const double2 u = g_unit_deg[(int)r - UNIT_DEG_MIN];
+        c = u.x; s = u.y;
+        return;
+    }
+    const double ang = __ddiv_rn(__dmul_rn((double)dir_deg, M_PI), 180.0);
+    c = cos(ang); s = sin(ang);
+}
+
 // Literal fp64 restatement of the per-pair predicates of in_zone (fish_mod.cpp:237-254) for a pair whose fp32
 // evaluation fell inside a rounding band.  dx,dy are exact (offsets are fp32, cell shifts are multiples of 200).
 // Products and sums are kept unfused so the operation order is the reference's.
@@ -121,8 +141,8 @@ __device__ __noinline__ unsigned exact_pair_bits(float oxi, float oyi, float dir
     const double sx = (double)((kcode % 3) - 1) * 200.0, sy = (double)((kcode / 3) - 1) * 200.0;
     const double x = __dadd_rn(__dsub_rn((double)oxj, (double)oxi), sx);
     const double y = __dadd_rn(__dsub_rn((double)oyj, (double)oyi), sy);
-    const double ang = __ddiv_rn(__dmul_rn((double)dir_deg, M_PI), 180.0);
-    const double c = cos(ang), s = sin(ang);
+    double c, s;
+    unit_vector_fp64(dir_deg, c, s);
     const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
     const double q = __ddiv_rn(__dadd_rn(__dmul_rn(c, x), __dmul_rn(s, y)), dist);
     const double angle = __ddiv_rn(__dmul_rn(acos(q), 180.0), M_PI);
@@ -268,7 +288,14 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
     const float near_r = fminf(fminf(fabsf(d - 15.f), fabsf(d - 100.f)), fabsf(d - 200.f));
     const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
-    const bool unc = (near_r < BAND_R || near_c < tb) && live;
+    // third bearing band: a neighbour EXACTLY dead ahead (integer-lattice states, the reference's own initial state,
+    // fish_mod.cpp:196-202).  The reference's fp64 cosine can round to 1 + 1e-16 there, acos() is NaN and the pair drops out
+    // of every count (fish_mod.cpp:252-254): only the literal fp64 evaluation can tell.  sin(bearing) = cross / d;
+    // an exactly collinear pair evaluates to <= 3e-7 in fp32 (unit-vector rounding), a non-collinear fp32 pair to >= 1e-6
+    // only 6e-7 of the time.
+    const float cross = fmaf(fc, dy, -fs * dx);
+    const bool ahead = fabsf(cross) * rinv < COLLINEAR_BAND && ca > 0.f;
+    const bool unc = (near_r < BAND_R || near_c < tb || ahead) && live;
     // classification values: the fp32 distance / bearing cosine, or -- for a borderline pair -- stand-ins that make the
     // comparisons below reproduce the literal fp64 predicates (only two floats cross the rare branch, and the five
     // flags are computed once, as predicates, after it)
@@ -288,7 +315,6 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     A.c_near += inter ? near_inc : 0;
     if (inter) {
         const bool al = in100 && !in15;
-        const float cross = fmaf(fc, dy, -fs * dx);
         const float crossA = fmaf(fc, qs, -fs * qc);
         const float dotA = fmaf(fc, qc, fs * qs);
         float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
@@ -387,6 +413,8 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
         bool unc = fabsf(d - 15.f) < BAND_R || fabsf(d - 100.f) < BAND_R || fabsf(d - 200.f) < BAND_R;
         unc = unc || fabsf(ca - COS165_F) < tb || fabsf(ca) < tb;
+        const float cross = fmaf(fc, dy, -fs * dx);
+        unc = unc || (fabsf(cross) * rinv < COLLINEAR_BAND && ca > 0.f);  // exactly dead ahead: see pair_math
         bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F, front = ca > 0.f;
         if (unc) {
             const uint32_t code = tj[k];
@@ -404,7 +432,6 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         if (STATS) A.inter++;
         // ---- turn contribution of this neighbour (fish_mod.cpp:316-351), radians
         const bool al = in100 && !in15;
-        const float cross = fmaf(fc, dy, -fs * dx);
         const float crossA = fmaf(fc, q.w, -fs * q.z);
         const float dotA = fmaf(fc, q.z, fs * q.w);
         float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
@@ -676,7 +703,15 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
         const bool moving = c1.x == 0;
         move_core(r, c0, c1.x, cx, cy, moving ? a.turn[i] : 0.f, moving ? a.cnt[i].w : 0, err, a.rolling, a.speed_norm_inv2);
         if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
-        else if (cx < 0 || cx >= a.g.lnx) { atomicOr(a.err, ERR_STEP_TOO_LONG); cx = max(0, min(cx, a.g.lnx - 1)); }
+        else {
+            // slabs: a fish may advance at most one column per step (the halo is one column wide, and with the edges-first
+            // update a fish of an interior column must not reach a boundary or halo column after the messages have left)
+            const int cx_old = mycell / ny;
+            if (cx < cx_old - 1 || cx > cx_old + 1 || cx < 0 || cx >= a.g.lnx) {
+                atomicOr(a.err, ERR_STEP_TOO_LONG);
+                cx = max(0, min(cx, a.g.lnx - 1));
+            }
+        }
         cy %= ny; if (cy < 0) cy += ny;
         const int newcell = cx * ny + cy;
         a.rec[i] = r;
@@ -1052,8 +1087,8 @@ __global__ void in_zone_generic_kernel(const ZoneArgs a) {
     if (i >= a.cell_start[a.g.own_c1]) return;
     const float4 me = a.rec[i];
     const int c = a.cell[i];
-    const double ang = __ddiv_rn(__dmul_rn((double)a.cold0[i].x, M_PI), 180.0);
-    const double cs = cos(ang), sn = sin(ang);
+    double cs, sn;
+    unit_vector_fp64(a.cold0[i].x, cs, sn);
     int count = 0;
     for (int k = 0; k < 9; ++k) {
         const int cc = stencil_cell(a.g, c, k);

@@ -42,7 +42,9 @@ FISH_HD uint32_t philox4x32_10_word0(uint32_t c0, uint32_t c1, uint32_t c2, uint
 }
 
 FISH_HD uint32_t word(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t id, uint32_t stream, uint32_t k) {
-    return philox4x32_10_word0(id, step, (stream & 0xFFu) | (k << 8), replicate, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // counter words: fish id | step | stream (8 bits) + the low 24 bits of k | replicate ^ the high 8 bits of k (k is a
+    // neighbour's id for tie draws: ids reach 2^28; identical to the plain packing for k < 2^24)
+    return philox4x32_10_word0(id, step, (stream & 0xFFu) | (k << 8), replicate ^ (k & 0xFF000000u), (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
 // integer in [a,b]; consumes words k0, k0+1, ... until one passes the rejection test

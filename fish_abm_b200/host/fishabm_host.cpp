@@ -60,9 +60,8 @@ long long Backend::sum_quality() {
 
 void Backend::push(const individuals& inds) {
     if (inds.n != n_ * reps_) throw Error(FISHABM_E_ARG, "individuals.n does not match the backend");
-    std::vector<double> speed((size_t)inds.n, inds.speed);  // the reference has one speed for the school (fish_mod.cpp:43)
     each([&](fishabm_ctx* c) {
-        return fishabm_set_state(c, inds.coords.data(), inds.dir.data(), speed.data(), inds.speed_factor.data(), inds.lag.data(),
+        return fishabm_set_state(c, inds.coords.data(), inds.dir.data(), inds.speed.data(), inds.speed_factor.data(), inds.lag.data(),
                                  inds.sample_rate.data(), inds.food_intake.data());
     });
 }
@@ -70,7 +69,7 @@ void Backend::push(const individuals& inds) {
 void Backend::pull(individuals& inds) {
     if (inds.n != n_ * reps_) inds.resize(n_ * reps_);
     each([&](fishabm_ctx* c) {
-        return fishabm_get_state(c, inds.coords.data(), inds.dir.data(), nullptr, inds.speed_factor.data(), inds.lag.data(),
+        return fishabm_get_state(c, inds.coords.data(), inds.dir.data(), inds.speed.data(), inds.speed_factor.data(), inds.lag.data(),
                                  inds.sample_rate.data(), inds.food_intake.data());
     });
 }
@@ -88,8 +87,8 @@ void initialize(Backend& b, individuals& inds, int n, int dim, double speed, con
     if (n != b.n()) throw Error(FISHABM_E_ARG, "initialize: n does not match the backend");
     b.each([&](fishabm_ctx* c) { return fishabm_initialize(c, speed); });  // every slab composes the same school and keeps its columns
     inds.resize(n * b.replicates());
-    inds.dim = dim; inds.speed = speed;
-    b.pull(inds);
+    inds.dim = dim;
+    b.pull(inds);  // speed[i] = speed for every fish, as initialize() sets it (fish_mod.cpp:190)
 }
 
 void get_environment(Backend& b, std::vector<int>& quality, const Structure& struc, const std::string& csv_path) {

@@ -24,14 +24,14 @@ struct Structure {  // class Structure, fish_mod.cpp:51-62
 
 struct individuals {  // class individuals, fish_mod.cpp:35-49 (colours / nfollow / sample[] are viewer-only or unused)
     int n = 0, dim = 2;
-    double speed = 5.0;
     std::vector<int> lag, sample_rate, food_intake;
+    std::vector<double> speed;   // double speed[num], fish_mod.cpp:43: one movement speed PER FISH (used per fish at :171-172)
     std::vector<double> dir, speed_factor;
     std::vector<double> coords;  // [n][2], x,y interleaved as in the reference
     void resize(int n_) {
         n = n_;
         lag.assign(n, 0); sample_rate.assign(n, 0); food_intake.assign(n, 0);
-        dir.assign(n, 0.0); speed_factor.assign(n, 1.0); coords.assign(2 * (size_t)n, 0.0);
+        speed.assign(n, 0.0); dir.assign(n, 0.0); speed_factor.assign(n, 1.0); coords.assign(2 * (size_t)n, 0.0);
     }
 };
 

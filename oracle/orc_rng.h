@@ -47,7 +47,8 @@ static inline void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2
 /* one 32-bit word for (seed, replicate, step, id, stream, k) */
 static inline uint32_t orc_word(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t id,
                                 uint32_t stream, uint32_t k) {
-    uint32_t ctr[4] = {id, step, (stream & 0xFFu) | (k << 8), replicate};
+    /* low 24 bits of k beside the stream, its high 8 bits folded into the replicate word (k = neighbour id for ties) */
+    uint32_t ctr[4] = {id, step, (stream & 0xFFu) | (k << 8), replicate ^ (k & 0xFF000000u)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);

@@ -236,7 +236,7 @@ def draw(seed: int, replicate: int, step: int, fish_id: int, stream: int, a: int
     k = k0
     while True:
         word = philox4x32_10((fish_id & 0xFFFFFFFF, step & 0xFFFFFFFF, (stream & 0xFF) | ((k << 8) & 0xFFFFFF00),
-                              replicate & 0xFFFFFFFF), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
+                              (replicate ^ (k & 0xFF000000)) & 0xFFFFFFFF), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
         prod = word * rng
         low = prod & 0xFFFFFFFF
         thr = ((1 << 32) - rng) % rng

@@ -54,13 +54,10 @@ def test_counts_vs_reference(golden, q100, case):
     want = golden[f"{case}_zone"]
     if exact_inputs:
         bad = (got != want).any(axis=1)
-        if case == "D":
-            # integer lattice: exactly collinear pairs whose fp64 cosine rounds above 1 are NaN-dropped by the
-            # reference; the fp32 path cannot see a 1e-16 excess.  Everything else must be exact.
-            O = Oracle(st.copy(), 2000, 2000, q100.copy())
-            assert bad.sum() <= 4, bad.sum()
-        else:
-            assert not bad.any(), np.nonzero(bad)[0][:10]
+        # case D is an integer lattice with integer headings: exactly collinear pairs whose fp64 cosine rounds above 1 are
+        # NaN-dropped by the reference.  pair_math sends every dead-ahead neighbour to the literal fp64
+        # evaluation (COLLINEAR_BAND), whose unit vector for integer headings is the host libm's: exact like every other case.
+        assert not bad.any(), (case, np.nonzero(bad)[0][:10], got[bad][:4], want[bad][:4])
         misc = np.stack([S.in_zone(200, 150.0), S.in_zone(90, 37.5), S.in_zone(360, 200)], 1)
         assert np.array_equal(misc, golden[f"{case}_zone_misc"])
         assert np.allclose(S.get_speed()[~bad], golden[f"{case}_get_speed"][~bad], rtol=0, atol=0)
@@ -78,11 +75,10 @@ def test_social_vs_reference(golden, q100, case):
     so = O.social(step=int(golden[f"{case}_step"]))
     turn, na, nl, nt = S.social()
     ok = (so["n_ties"] == 0) & (so["knife"] == 0)
-    if case == "D":
-        ok &= (na == so["n_avoid"]) & (nl == so["n_align"]) & (nt == so["n_attract"])
-        assert ok.mean() > 0.9
-    else:
-        assert np.array_equal(na, so["n_avoid"]) and np.array_equal(nl, so["n_align"]) and np.array_equal(nt, so["n_attract"])
+    # measured on these fixtures: no fish of A, A2, B, C, E consumes a tie draw or sits on a knife edge (so nothing is
+    # masked there: 60 of 60 fish of the default lattice start are checked); D has one knife-edge fish
+    assert (~ok).sum() <= (1 if case == "D" else 0)
+    assert np.array_equal(na, so["n_avoid"]) and np.array_equal(nl, so["n_align"]) and np.array_equal(nt, so["n_attract"])
     # the same fp32-rounded state on both sides
     assert np.abs(np.deg2rad(turn - so["turn"]))[ok].max() < TOL_RAD
     same_inputs = np.array_equal(to32(st).coords, st.coords) and np.array_equal(to32(st).dir, st.dir)
@@ -132,6 +128,19 @@ def test_draws_match_oracle_table(golden):
         if stream == 99:
             continue
         assert S.draw(int(stream), int(step), int(fid), int(a), int(b)) == val
+
+
+def test_draws_with_wide_k_match_oracle():
+    """tie draws are keyed by the neighbour's id (k): ids beyond 2^24 must not wrap into each other"""
+    from oracle.pyoracle import draw
+    S = School(n=60, seed=0xABCDEF12345)
+    seen = set()
+    for k in (0, 1, (1 << 24) - 1, 1 << 24, (1 << 24) + 1, (1 << 27) + 12345, (1 << 28) - 1):
+        vals = tuple(S.draw(_lib.STREAM_RANDOMWALK, step, 17, -45, 45, k=k) for step in range(24))
+        want = tuple(draw(0xABCDEF12345, 0, step, 17, _lib.STREAM_RANDOMWALK, -45, 45, k0=k) for step in range(24))
+        assert vals == want, k
+        seen.add(vals)
+    assert len(seen) == 7   # seven distinct 24-draw sequences: no two k share a counter
 
 
 # ---- against the oracle on seeded states ---------------------------------------------------------------------------

@@ -59,3 +59,17 @@ def test_draw_ranges_and_uniformity():
     assert v.min() == -10 and v.max() == 10
     counts = np.bincount(v + 10, minlength=21)
     assert np.abs(counts - 1000).max() < 150
+
+
+def test_wide_k_is_folded_into_the_replicate_word():
+    """k >= 2^24 (a neighbour id of a very large school in a tie draw) must address its own counter: the C oracle and the
+    pure-Python restatement agree, and k and k + 2^24 differ"""
+    import ctypes as C
+    from oracle.pyoracle import Oracle, draw
+    L = Oracle.lib()
+    L.orc_draw_export.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    a = [L.orc_draw_export(99, 3, s, 5, 2, 7, -45, 45) for s in range(32)]
+    b = [L.orc_draw_export(99, 3, s, 5, 2, 7 + (1 << 24), -45, 45) for s in range(32)]
+    assert a != b
+    assert b == [draw(99, 3, s, 5, 2, -45, 45, k0=7 + (1 << 24)) for s in range(32)]
+    assert a == [draw(99, 3, s, 5, 2, -45, 45, k0=7) for s in range(32)]
