@@ -111,6 +111,28 @@ def ncu_capture(kernel_prefix: str):
     return None
 
 
+def workload_string(n: int, w: int) -> str:
+    """config.workload, identical in both arms (ours / reference) for the same school"""
+    tag = {N_C3: "C3: ", N_C4: "C4: "}.get(n, "")
+    return f"{tag}N={n} school, W=H={w} periodic, cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0"
+
+
+def stratified_ids(lag: np.ndarray, k: int, seed: int) -> np.ndarray:
+    """k focal fish whose moving (lag == 0, 8 all-pairs passes) : lagged (3 passes) mix equals the school's: a plain random
+    sample of a few dozen fish makes the extrapolated agent-steps/s swing by +-50 % with the mix alone"""
+    rng = np.random.default_rng(seed)
+    moving, lagged = np.nonzero(lag == 0)[0], np.nonzero(lag != 0)[0]
+    km = int(round(k * len(moving) / len(lag)))
+    km = min(max(km, 1 if len(moving) else 0), len(moving))
+    ids = np.concatenate([rng.choice(moving, km, replace=False), rng.choice(lagged, min(k - km, len(lagged)), replace=False)])
+    return rng.permutation(ids).astype(np.int32)
+
+
+def build_info() -> dict:
+    from fish_abm_b200 import build as b
+    return {"libfishabm": b.LAST["decision"], "nvcc": b.LAST["nvcc"] or b.nvcc_version()}
+
+
 def flops_alg(cand: float, inter: float) -> float:
     """13 flops per candidate pair + 20 per interacting pair"""
     return 13.0 * cand + 20.0 * inter
@@ -136,8 +158,9 @@ def reference_arm(args, rank: int, world: int):
     d = synth.uniform_state(n, w, w, seed=0x5EED)
     cores = min(os.cpu_count() or 1, 32)
     kind = "reference" if (n == N_C3 and RefLib.available(N_C3)) else "port"
-    k = 2 * cores if n <= N_C3 else cores
-    ids = np.random.default_rng(1).choice(n, k, replace=False).astype(np.int32)
+    # >= 16 focal fish per thread and step at C3 (about 2.5 s of all-core work per step); a C4-sized fish costs 17x more
+    k = 16 * cores if n <= N_C3 else 4 * cores
+    ids = stratified_ids(d["lag"], k, seed=1)
     if kind == "reference":
         R = RefLib(N_C3)
         R.set_world(w, w)
@@ -148,17 +171,17 @@ def reference_arm(args, rank: int, world: int):
         used = O.time_focal(ids[:1])[1]   # threads OpenMP really gives us
         cores = used
         run = lambda: O.time_focal(ids)[0]
-    if n > N_C3:   # a C4-sized step is ~5-7 s of all-core work: keep the whole arm to about a minute and a half
-        args.steps, args.warmup = min(args.steps, 8), min(args.warmup, 1)
+    if n > N_C3:   # a C4-sized step is ~15-20 s of all-core work: keep the whole arm to about a minute and a half
+        args.steps, args.warmup = min(args.steps, 4), min(args.warmup, 1)
+    else:
+        args.steps, args.warmup = min(args.steps, 10), min(args.warmup, 1)
     for _ in range(min(args.warmup, 2)):
         run()
     secs = [run() for _ in range(args.steps)]
     tot = float(np.sum(secs))
     value = k * args.steps / tot
-    cfg = {"workload": f"C3: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C3 else
-                       (f"C4: N={n} school, W=H={w}, rho=5e-4, quality.csv tiled" if n == N_C4 else f"N={n}, W=H={w}"),
-           "n_fish": n, "world": w, "l2": "n/a (CPU)"}
-    sample = (f"{k} focal fish per step on the full {n}-fish frozen state, each doing the reference's own per-fish work of "
+    cfg = {"workload": workload_string(n, w), "n_fish": n, "world": w, "l2": "n/a (CPU)"}
+    sample = (f"{k} focal fish per step (moving : lagged mix as in the school) on the full {n}-fish frozen state, each doing the reference's own per-fish work of "
               f"move()+sample() (8 all-pairs passes if lag==0 else 3); agent-steps/s = focal fish / seconds (extrapolation, "
               f"the O(N^2) step itself is ~days)")
     line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
@@ -180,13 +203,119 @@ def cpu_baseline_leg(n, w, d, budget_s=12.0):
     else:
         O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, None, seed=1)
         run = lambda ids: O.time_focal(ids)[0]
-    rng = np.random.default_rng(2)
-    t1 = run(rng.choice(n, cores, replace=False).astype(np.int32))
-    k = int(max(cores, min(64 * cores, cores * budget_s / max(t1, 1e-3))))
-    secs = run(rng.choice(n, k, replace=False).astype(np.int32))
+    t1 = run(stratified_ids(d["lag"], 2 * cores, seed=2))
+    k = int(max(2 * cores, min(64 * cores, 2 * cores * budget_s / max(t1, 1e-3))))
+    secs = run(stratified_ids(d["lag"], k, seed=3))
     return {"value": k / secs, "unit": "agent-steps/s", "cores": cores, "kind": kind,
-            "sample": f"{k} focal fish of the {n}-fish state in {secs:.1f} s on {cores} host threads (per-fish work of move()+sample(): "
+            "sample": f"{k} focal fish (moving : lagged mix as in the school) of the {n}-fish state in {secs:.1f} s on {cores} host threads (per-fish work of move()+sample(): "
                       f"8 all-pairs passes if lag==0 else 3), extrapolated to agent-steps/s = focal fish / seconds"}
+
+
+def whole_school_leg(n: int, device: int, warmup: int, steps: int, d=None, q=None, keep: bool = False):
+    """one whole school of n fish on ONE GPU: device-timed throughput of `steps` steps (+ the trailing sample pass).  Used for
+    the 1-GPU base of the C4 scaling curve (N=1 line: c4_one_gpu; N>1 lines: every rank runs it as the parity reference of
+    its slab).  keep=True returns the live School as well."""
+    from fish_abm_b200 import School, synth
+    w = synth.world_size_for(n)
+    if d is None:
+        d = synth.uniform_state(n, w, w, seed=0x5EED)
+    if q is None:
+        q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+        q = synth.tile_quality(q100, w, w)
+    S = School(n=n, w=w, h=w, seed=0x5EED, device=device)
+    S.set_state(**d)
+    S.set_quality(q)
+    for _ in range(warmup):
+        S.step(1)
+    S.flush()
+    S.step(steps)
+    ms = S.last_step_ms()
+    nb_ms, nb_l = S.last_neighbour_ms()
+    S.flush()
+    ms += S.last_step_ms()
+    a, b = S.last_neighbour_ms(); nb_ms += a; nb_l += b
+    out = {"value": n * steps / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "neighbour_ms_per_launch": nb_ms / max(nb_l, 1), "workload": workload_string(n, w),
+           "l2": "state larger than L2" if n * 76 > (126 << 20) else "state fits L2, not flushed"}
+    if keep:
+        return out, S
+    S.close()
+    return out
+
+
+def small_configs_leg(device: int, with_cpu: bool):
+    """BASELINE.json configs[0] / configs[1] next to the reference itself: the verbatim,
+    single-threaded fish_mod.cpp (move()+sample(), full sequential steps; -O2 and, as shipped by fishmod_compile.sh:1, -O0)
+    on this box's host, beside the GPU's ms per step for the same school."""
+    from fish_abm_b200 import Ensemble, School, synth
+    from oracle.pyoracle import RefLib, State
+    qpath = os.path.join(ROOT, "tests", "golden", "quality.csv")
+    q100 = np.loadtxt(qpath, delimiter=",", dtype=np.int32)
+    out = {}
+    # ---- GPU
+    with School(n=60, w=2000, h=2000, seed=1, device=device, speed_norm=60.0) as S:      # C1: the reference's default school
+        S.initialize(5.0); S.set_quality(q100)
+        S.step(50); S.flush()
+        S.step(500); ms = S.last_step_ms(); S.flush(); ms += S.last_step_ms()
+        out["C1_n60"] = {"gpu_ms_per_step_cell_list": ms / 500}
+    with Ensemble(1, n=60, seed=1, device=device, speed_norm=60.0) as E:
+        E.initialize(5.0); E.set_quality(q100)
+        E.step(50)
+        E.step(500)
+        out["C1_n60"]["gpu_ms_per_step_ensemble_kernel"] = E.last_step_ms() / 500
+    for n in (1000, 10000):                                                                # C2 and the point in between
+        d = synth.uniform_state(n, 2000, 2000, seed=3)
+        with School(n=n, w=2000, h=2000, seed=1, device=device) as S:
+            S.set_state(**d); S.set_quality(q100)
+            S.step(20); S.flush()
+            S.step(100); ms = S.last_step_ms(); S.flush(); ms += S.last_step_ms()
+            out[("C2_n10000" if n == 10000 else f"n{n}")] = {"gpu_ms_per_step_cell_list": ms / 100}
+    if not with_cpu:
+        return out
+    # ---- CPU: the unmodified reference, one thread, whole sequential steps
+    def ref_ms(n, suffix, steps):
+        if not RefLib.available(n, suffix):
+            return None
+        R = RefLib(n, suffix)
+        R.set_world(2000, 2000)
+        if n == 60:
+            R.initialize(60, 5.0, 1)
+        else:
+            R.set_state(State(**synth.uniform_state(n, 2000, 2000, seed=3)))
+        R.get_environment(os.path.dirname(qpath))
+        R.rng(1, 0, 0)
+        secs, _, _ = R.run(steps, 0, log_sumq=False)
+        return 1e3 * secs / steps
+    out["C1_n60"].update(cpu_ref_ms_per_step_O2=ref_ms(60, "", 500), cpu_ref_ms_per_step_O0=ref_ms(60, "_O0", 200))
+    out["n1000"].update(cpu_ref_ms_per_step_O2=ref_ms(1000, "", 4), cpu_ref_ms_per_step_O0=ref_ms(1000, "_O0", 2))
+    out["C2_n10000"].update(cpu_ref_ms_per_step_O2=ref_ms(10000, "", 1), cpu_ref_ms_per_step_O0=None,
+                            note="-O0 at N=10k is ~3.2x the -O2 figure (the measured N=60 / N=1000 ratio); not run to keep the bench short")
+    out["cpu"] = {"threads": 1, "what": "unmodified fish_mod.cpp (oracle/_ref), move()+sample() as in its main loop, whole sequential steps",
+                  "model": next((l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")), "unknown"),
+                  "host_cores": os.cpu_count()}
+    return out
+
+
+def ensemble_key(device: int, schools: int, steps: int = 20):
+    """BASELINE.json configs[4] on this rank's GPU: `schools` replicate schools of 200 fish sweeping speed (2.5..20),
+    sample-rate reset (15/30/45) and fed speed factor (0.25/0.5/0.75) per school; K steps in ONE launch"""
+    from fish_abm_b200 import Ensemble
+    q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
+    n = 200
+    E = Ensemble(schools, n=n, seed=0x5EED, replicate0=0, device=device, speed_norm=float(n))
+    E.initialize(5.0)
+    g = E.get_state()
+    g["speed"][:] = np.array([2.5, 5, 7.5, 10, 12.5, 15, 17.5, 20])[(np.arange(schools) % 8)][:, None]
+    E.set_state(**g)
+    E.set_quality(q100)
+    swept = E.sweep_default() if hasattr(E, "sweep_default") else None
+    E.step(3)
+    E.step(steps)
+    ms = E.last_step_ms()
+    eaten = int((3499 - np.asarray(E.sum_array())).sum())
+    E.close()
+    return {"value": schools * n * steps / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms / steps, "schools": schools, "n_fish": n,
+            "steps": steps, "school_steps_per_sec": schools * steps / (ms * 1e-3), "food_eaten": eaten, "swept": swept or "speed 2.5..20"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -316,15 +445,25 @@ def ours(args, rank: int, world: int, local_rank: int):
 
     cpu = cpu_baseline_leg(n, w, d) if not args.no_cpu_baseline else None
     S.close()
+    del flush
+    torch.cuda.empty_cache()
+    # the 1-GPU base of the C4 scaling curve (the N>1 lines run C4), the small configurations, and configs[4]
+    extra = {}
+    if n == N_C3 and not args.fish:
+        extra["c4_one_gpu"] = whole_school_leg(N_C4, local_rank, warmup=3, steps=10)
+        extra["small_configs"] = small_configs_leg(local_rank, with_cpu=not args.no_cpu_baseline)
+        if not args.no_ensemble:
+            extra["ensemble"] = ensemble_key(local_rank, args.schools)
     line = {"metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C3: N={n} school, W=H={w} periodic, cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0"
-                       if n == N_C3 else f"N={n} school, W=H={w}", "n_fish": n, "world": w,
+            "scaling_note": "the N=1 line is C3 (1M fish); the N>1 lines are C4 (16.8M fish, strong scaling over 2/4/8 GPUs) whose 1-GPU base "
+                            "is c4_one_gpu below (and is re-measured inside every N>1 line)",
+            "config": {"workload": workload_string(n, w), "n_fish": n, "world": w,
                        "l2": "flushed between steps (256 MiB write)" if flush is not None else "state larger than L2",
                        "timing": "CUDA events on the library's stream around each fishabm_step(1); K steps + the trailing sample pass"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "cpu_baseline": cpu, "parity_spot_check": parity}
+            "cpu_baseline": cpu, "parity_spot_check": parity, "build": build_info(), **extra}
     print(json.dumps(line), flush=True)
 
 
@@ -393,6 +532,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="school", choices=["school", "ensemble"])
     ap.add_argument("--schools", type=int, default=65536)
+    ap.add_argument("--one-transport", action="store_true", help="N>1: skip the second slab transport")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the configs[4] ensemble key")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

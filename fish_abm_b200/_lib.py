@@ -50,7 +50,7 @@ SYMBOLS = [
     "fishabm_slab_get_info", "fishabm_slab_unique_id", "fishabm_slab_connect", "fishabm_slab_begin_step",
     "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy", "fishabm_slab_get_endpoint",
     "fishabm_slab_attach", "fishabm_step_enqueue", "fishabm_wait", "fishabm_set_state_owned", "fishabm_get_state_owned",
-    "fishabm_create_environment", "fishabm_check_fp64",
+    "fishabm_create_environment", "fishabm_check_fp64", "fishabm_enable_phase_timing", "fishabm_last_phase_ms",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -97,6 +97,8 @@ def load():
     L.fishabm_last_pass_stats.argtypes = [vp, C.POINTER(PassStats)]
     L.fishabm_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.fishabm_enable_stats.argtypes = [vp, i32]
+    L.fishabm_enable_phase_timing.argtypes = [vp, i32]
+    L.fishabm_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float * 4), C.POINTER(i32)]
     L.fishabm_averageturn.argtypes = [vp, i32, i32]
     L.fishabm_averageturn.restype = dbl
     L.fishabm_correctangle.argtypes = [dbl]

@@ -31,9 +31,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+LAST = {"decision": None, "nvcc": None}   # what build_lib did in this process (bench.py prints it)
+
+
+def nvcc_version() -> str:
+    try:
+        out = subprocess.run([nvcc_path(), "--version"], capture_output=True, text=True).stdout
+        return next((l.split("release")[-1].strip() for l in out.splitlines() if "release" in l), "unknown")
+    except Exception:  # noqa: BLE001
+        return "unavailable"
+
+
 def build_lib(force: bool = False, verbose: bool = False, extra=()) -> str:
     if not force and not needs_build():
+        LAST.update(decision="reused (libfishabm.so newer than every source)", nvcc=None)
         return LIB
+    LAST.update(decision="rebuilt", nvcc=nvcc_version())
     cmd = [nvcc_path(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
            "-ccbin", shutil.which("g++") or "g++", "-I", os.path.join(HERE, "..", "include"), *extra,
            *sources(), "-o", LIB, "-lcudart"]

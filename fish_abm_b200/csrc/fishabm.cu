@@ -41,6 +41,10 @@ struct fishabm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> nb_events;  // around each neighbour kernel of the last call
     int nb_events_used = 0;
+    // optional phase timing of fishabm_step (fishabm_enable_phase_timing): 5 events per step
+    bool phases_on = false;
+    std::vector<cudaEvent_t> ph_events;
+    int ph_steps = 0;
     int n = 0;            // fish ids are 0..n-1 (the whole school, also in slab mode)
     int cap = 0;          // entries the sorted arrays can hold (= n for a whole school)
     Grid g;               // local grid (kernels.cuh)
@@ -382,8 +386,24 @@ int update_pass(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_mo
     return finish_move(ctx, il, ir);
 }
 
+// phase boundaries of one step: 0 start, 1 after the neighbour pass, 2 after update (+publish), 3 after the exchange, 4 after the sort
+constexpr int PH_PER_STEP = 5, PH_MAX_STEPS = 512;
+int phase_mark(fishabm_ctx* ctx, int k) {
+    if (!ctx->phases_on || ctx->ph_steps >= PH_MAX_STEPS) return 0;
+    const size_t idx = (size_t)ctx->ph_steps * PH_PER_STEP + k;
+    while (ctx->ph_events.size() <= idx) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        try { ctx->ph_events.push_back(e); } catch (...) { cudaEventDestroy(e); return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
+    }
+    CK(cudaEventRecord(ctx->ph_events[idx], ctx->stream));
+    if (k == PH_PER_STEP - 1) ctx->ph_steps++;
+    return 0;
+}
+
 int begin_timed(fishabm_ctx* ctx) {
     ctx->nb_events_used = 0;
+    ctx->ph_steps = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     return 0;
 }
@@ -698,6 +718,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
     cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);
     for (auto& pr : c->nb_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : c->ph_events) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -1182,9 +1203,11 @@ static int step_first_half(fishabm_ctx* ctx) {
     const uint32_t s = ctx->step;
     if (ctx->pending_sample) {  // sample(s-1) and move(s) share one neighbour pass
         if ((rc = neighbour_pass(ctx, 1, true, s - 1, s, true))) return rc;
+        if ((rc = phase_mark(ctx, 1))) return rc;
         return update_launch(ctx, true, true, s);
     }
     if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
+    if ((rc = phase_mark(ctx, 1))) return rc;
     return update_launch(ctx, false, true, s);
 }
 
@@ -1192,10 +1215,14 @@ static int step_untimed(fishabm_ctx* ctx, int nsteps) {
     // move(s); { sample(s+t-1) + move(s+t) } ...; the trailing sample stays pending (flush_pending)
     int rc;
     for (int t = 0; t < nsteps; ++t) {
+        if ((rc = phase_mark(ctx, 0))) return rc;
         if ((rc = step_first_half(ctx))) return rc;
+        if ((rc = phase_mark(ctx, 2))) return rc;
         unsigned char *il = nullptr, *ir = nullptr;
         if (ctx->slab && (rc = exchange(ctx, &il, &ir))) return rc;
+        if ((rc = phase_mark(ctx, 3))) return rc;
         if ((rc = finish_move(ctx, il, ir))) return rc;
+        if ((rc = phase_mark(ctx, 4))) return rc;
         ctx->pending_sample = true;
         ctx->step += 1;
     }
@@ -1474,6 +1501,25 @@ int fishabm_last_neighbour_ms(const fishabm_ctx* ctx, float* ms, int32_t* launch
     }
     *ms = total;
     if (launches) *launches = ctx->nb_events_used;
+    return 0;
+}
+
+int fishabm_enable_phase_timing(fishabm_ctx* ctx, int32_t on) {
+    if (!ctx) return FISHABM_E_ARG;
+    ctx->phases_on = on != 0;
+    ctx->ph_steps = 0;
+    return 0;
+}
+
+int fishabm_last_phase_ms(const fishabm_ctx* ctx, float* ms4, int32_t* steps) {
+    if (!ctx || !ms4) return FISHABM_E_ARG;
+    for (int k = 0; k < 4; ++k) ms4[k] = 0.f;
+    for (int t = 0; t < ctx->ph_steps; ++t)
+        for (int k = 0; k < 4; ++k) {
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, ctx->ph_events[(size_t)t * PH_PER_STEP + k], ctx->ph_events[(size_t)t * PH_PER_STEP + k + 1]) == cudaSuccess) ms4[k] += v;
+        }
+    if (steps) *steps = ctx->ph_steps;
     return 0;
 }
 

@@ -247,6 +247,17 @@ class School:
     def enable_stats(self, on: bool = True):
         self.L.fishabm_enable_stats(self.ctx, int(on))
 
+    PHASES = ("neighbour", "update", "exchange", "sort")
+
+    def enable_phase_timing(self, on: bool = True):
+        self.L.fishabm_enable_phase_timing(self.ctx, int(on))
+
+    def last_phase_ms(self) -> dict:
+        """device ms by phase, summed over the steps of the last step() call (include/fishabm.h)"""
+        ms, k = (C.c_float * 4)(), C.c_int32(0)
+        self.L.fishabm_last_phase_ms(self.ctx, C.byref(ms), C.byref(k))
+        return dict(zip(self.PHASES, (float(v) for v in ms)), steps=int(k.value))
+
     def last_pass_stats(self) -> dict:
         s = _lib.PassStats()
         self._ck(self.L.fishabm_last_pass_stats(self.ctx, C.byref(s)))

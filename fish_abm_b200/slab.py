@@ -219,11 +219,31 @@ class LocalSlabs:
 
 
 # ---- the multi-GPU benchmark leg (bench.py --gpus N, N > 1) ----------------------------------------------------------------
+def compare_with_whole_school(S, g: dict, gq: np.ndarray) -> dict:
+    """this rank's slab against a whole-school run of the same steps: every field of every fish the slab owns and every
+    food cell of its columns must be bit-identical (id-ordered feed, fish_mod.cpp:541,563-574, and migration are what can
+    break across ranks).  g / gq: get_state() / get_quality() of the whole school."""
+    own = S.get_state_owned()
+    ids = own["ids"]
+    bad = np.zeros(len(ids), bool)
+    per_field = {}
+    for k in School.FIELDS:
+        a, b = own[k], g[k][ids]
+        neq = (a != b).reshape(len(ids), -1).any(axis=1)
+        per_field[k] = int(neq.sum())
+        bad |= neq
+    sq = S.get_quality()
+    m = sq >= 0
+    return {"owned": int(len(ids)), "fish_mismatches": int(bad.sum()), "unique_ids": int(len(np.unique(ids)) == len(ids)),
+            "food_cells": int(m.sum()), "food_mismatches": int((sq[m] != gq[m]).sum()), "per_field": per_field}
+
+
 def run_slab_bench(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
     from . import synth
-    from bench import N_C4, ClockSampler, measured_peaks, flops_alg, FP32_LANES_PER_SM, ROOT
+    from bench import (N_C4, ClockSampler, measured_peaks, flops_alg, FP32_LANES_PER_SM, ROOT, workload_string, whole_school_leg,
+                       build_info, ensemble_key)
 
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.fish or N_C4
@@ -231,50 +251,110 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
     q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
     d = synth.uniform_state(n, w, w, seed=0x5EED)   # every rank composes the same whole-school state ...
     q = synth.tile_quality(q100, w, w)
-    S = DistributedSchool(dist, rank, world, local_rank, n=n, w=w, h=w, seed=0x5EED)
-    S.set_state(**d)                                 # ... and keeps its own columns
-    S.set_quality(q)
-    info = S.slab_info()
-    del q
+    P = 5                                            # steps of the phase-timed run
+    T = args.warmup + args.steps + 1 + P             # steps every arm ends at (the parity check compares states at T)
 
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(*v):
+        t = torch.tensor(v, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def allsum(*v):
+        t = torch.tensor(v, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def timed_arm(transport: str, detailed: bool):
+        """warm-up, K timed steps (device events, max over ranks), then up to step T; returns the open slab + numbers"""
+        S = DistributedSchool(dist, rank, world, local_rank, transport=transport, n=n, w=w, h=w, seed=0x5EED)
+        S.set_state(**d)                             # ... and keeps its own columns
+        S.set_quality(q)
+        info = S.slab_info()
+        for _ in range(args.warmup):
+            S.step(1)
+        S.flush()
+        barrier()
+        launches0 = S.launch_count()
+        # K steps in one library call per rank: neighbour pass, update+pack, exchange, ingest, sort, all on the library's
+        # stream with no host synchronisation in between; the trailing sample() is part of the K steps
+        t0 = time.perf_counter()
+        S.step(args.steps)
+        ms = S.last_step_ms()
+        nb_ms, nb_l = S.last_neighbour_ms()
+        S.flush()
+        ms += S.last_step_ms()
+        a, b = S.last_neighbour_ms(); nb_ms += a; nb_l += b
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = S.launch_count() - launches0
+        ms_max, wall_max = allmax(ms, wall * 1e3)
+        res = {"transport": S.transport, "value": n * args.steps / (ms_max * 1e-3), "ms_per_step": ms_max / args.steps,
+               "wall_ms_per_step_max": wall_max / args.steps, "launches": launches, "nb_ms": nb_ms, "nb_l": nb_l, "info": info, "ms_max": ms_max}
+        if detailed:
+            # pair counters of one pass for the roofline line (rank-local work, summed over ranks)
+            S.enable_stats(True)
+            S.step(1)
+            res["stats"] = S.last_pass_stats()
+            S.flush()
+            S.enable_stats(False)
+            # where a step goes on every rank: device time by phase over P steps
+            S.enable_phase_timing(True)
+            barrier()
+            S.step(P)
+            ph = S.last_phase_ms()
+            S.enable_phase_timing(False)
+            S.flush()
+            mine = torch.tensor([ph["neighbour"] / P, ph["update"] / P, ph["exchange"] / P, ph["sort"] / P, float(S.slab_info()["owned"])],
+                                dtype=torch.float64, device="cuda")
+            parts = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            tab = np.array([p.cpu().numpy() for p in parts])
+            res["per_rank"] = {"neighbour_ms": tab[:, 0].round(4).tolist(), "update_ms": tab[:, 1].round(4).tolist(),
+                               "exchange_wait_ms": tab[:, 2].round(4).tolist(), "sort_ms": tab[:, 3].round(4).tolist(),
+                               "owned_fish": tab[:, 4].astype(int).tolist(),
+                               "max": dict(zip(("neighbour_ms", "update_ms", "exchange_wait_ms", "sort_ms"), tab[:, :4].max(axis=0).round(4).tolist())),
+                               "mean": dict(zip(("neighbour_ms", "update_ms", "exchange_wait_ms", "sort_ms"), tab[:, :4].mean(axis=0).round(4).tolist())),
+                               "how": f"fishabm_last_phase_ms over {P} steps after the timed run (CUDA events on each rank's stream)"}
+        else:
+            S.step(1 + P)
+            S.flush()
+        assert S.step_index == T, (S.step_index, T)
+        return S, res
+
     clocks = ClockSampler(local_rank)   # sampled from the warm-up through the end of the timed steps
     clocks.start()
-    for _ in range(args.warmup):
-        S.step(1)
-    S.flush()
-    barrier()
-    launches0 = S.launch_count()
-    # K steps in one library call per rank: neighbour pass, update+pack, NCCL exchange, ingest, sort, all on the
-    # library's stream with no host synchronisation in between; the trailing sample() is part of the K steps
-    t0 = time.perf_counter()
-    S.step(args.steps)
-    ms = S.last_step_ms()
-    nb_ms, nb_l = S.last_neighbour_ms()
-    S.flush()
-    ms += S.last_step_ms()
-    a, b = S.last_neighbour_ms(); nb_ms += a; nb_l += b
-    barrier()
-    wall = time.perf_counter() - t0
-    launches = S.launch_count() - launches0
+    S, main = timed_arm(None, detailed=True)
     clk = clocks.stop()
-    t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, wall_max = float(t[0]), float(t[1])
-
-    # pair counters of one pass for the roofline line (rank-local work, summed over ranks)
-    S.enable_stats(True)
-    S.step(1)
-    st = S.last_pass_stats()
-    S.flush()
-    S.enable_stats(False)
-    c = torch.tensor([st["candidates"], st["interacting"], st["focal"], launches, nb_ms, nb_l, info["owned"]], dtype=torch.float64, device="cuda")
+    info, st = main["info"], main["stats"]
+    c = torch.tensor([st["candidates"], st["interacting"], st["focal"], main["launches"], main["nb_ms"], main["nb_l"], info["owned"]],
+                     dtype=torch.float64, device="cuda")
     cs = c.clone(); dist.all_reduce(cs, op=dist.ReduceOp.SUM)
     cm = c.clone(); dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+
+    # ---- parity on real hardware: every rank runs the WHOLE school for the same T steps on its own GPU (2.2 GB) and
+    # compares the fish and food columns its slab owns bit for bit; rank 0's timing of that run is the 1-GPU base of the
+    # scaling curve
+    one_gpu, G = whole_school_leg(n, local_rank, args.warmup, args.steps, d=d, q=q, keep=True)
+    G.step(1 + P)
+    G.flush()
+    assert G.step_index == T
+    g, gq = G.get_state(), G.get_quality()
+    G.close()
+
+    def parity_of(Sx):
+        r = compare_with_whole_school(Sx, g, gq)
+        tot = allsum(r["owned"], r["fish_mismatches"], r["food_cells"], r["food_mismatches"], 1 - r["unique_ids"])
+        return {"against": f"a whole-school run of the same {T} steps on one GPU (every rank, its own copy)", "steps": T,
+                "fish_compared": int(tot[0]), "fish_mismatches": int(tot[1]), "fields": list(School.FIELDS),
+                "food_cells_compared": int(tot[2]), "food_mismatches": int(tot[3]), "ranks_with_duplicate_ids": int(tot[4]),
+                "all_fish_accounted_for": bool(int(tot[0]) == n)}
+
+    parity = parity_of(S)
 
     # end to end through the C ABI, host buffers (pinned) in and out every step: each rank uploads ITS fish
     # (fishabm_set_state_owned: ids + state, then one halo exchange), steps, downloads its fish (which migration has
@@ -299,12 +379,29 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
         S.sum_array()
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s, moved_bytes / e2e_steps], dtype=torch.float64, device="cuda")
-    tmax = te.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tsum = te.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    te = tmax
-    h2d = d2h = int(float(tsum[1]))
+    e2e_max, = allmax(e2e_s)
+    h2d = d2h = int(allsum(moved_bytes / e2e_steps)[0])
+    transport_main = S.transport
     S.close()
+    del bufs
+
+    # ---- the other transport (north_star names NCCL send/recv; the default is the peer-memory inboxes): same steps, same check
+    other = "nccl" if transport_main == "p2p" else "p2p"
+    transports = {transport_main: {"value": main["value"], "ms_per_step": main["ms_per_step"], "parity": parity}}
+    if not getattr(args, "one_transport", False):
+        try:
+            S2, r2 = timed_arm(other, detailed=False)
+            transports[r2["transport"]] = {"value": r2["value"], "ms_per_step": r2["ms_per_step"], "parity": parity_of(S2)}
+            S2.close()
+        except Exception as e:  # noqa: BLE001
+            transports[other] = {"error": str(e)[:300]}
+    ens = ensemble_key(local_rank, max(1, args.schools // world)) if not getattr(args, "no_ensemble", False) else None
+    if ens is not None:   # replicates are independent: every rank ran schools/world of them, slowest rank sets the time
+        ems, = allmax(ens["ms_per_step"])
+        eat, = allsum(ens["food_eaten"])
+        tot = ens["schools"] * world
+        ens = dict(ens, schools=tot, ms_per_step=ems, value=tot * ens["n_fish"] / (ems * 1e-3), school_steps_per_sec=tot / (ems * 1e-3),
+                   food_eaten=int(eat), scaling="weak: replicates split across the GPUs, no communication")
     if rank == 0:
         peaks, how = measured_peaks()
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
@@ -312,22 +409,27 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
         per_launch_ms = float(cm[4]) / max(float(cm[5]), 1.0)           # slowest rank's average neighbour launch
         flops = flops_alg(float(cs[0]), float(cs[1])) / world            # per rank, per launch
         achieved = flops / (per_launch_ms * 1e-3) / 1e12
-        line = {"metric": "agent_steps_per_sec", "value": n * args.steps / (ms_max * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        value = main["value"]
+        line = {"metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C4: N={n} school, W=H={w} periodic, {world} x-slabs with 200-unit halos + migration ({S.transport} transport), "
-                                       f"cell-list r=200, rho=5e-4, quality.csv tiled, 60% fish lagged at t=0" if n == N_C4 else f"N={n}, W=H={w}, {world} slabs",
-                           "n_fish": n, "world": w, "parallelism": f"slab{world}", "l2": "per-rank state larger than L2" if n // world * 76 > (126 << 20) else "state fits L2, not flushed",
+                "scaling_note": "strong scaling of C4 (16.8M fish) over the GPUs; its 1-GPU base is c4_one_gpu, measured in this same run",
+                "config": {"workload": workload_string(n, w), "n_fish": n, "world": w, "parallelism": f"slab{world}",
+                           "decomposition": f"{world} x-slabs with 200-unit halo columns + migration", "transport": transport_main,
+                           "l2": "per-rank state larger than L2" if n // world * 76 > (126 << 20) else "state fits L2, not flushed",
                            "timing": "CUDA events on each rank's library stream around fishabm_step(K) + the trailing sample pass, max over ranks",
-                           "message_bytes_per_neighbour_per_step": info["message_bytes"], "wall_ms_per_step_max": wall_max / args.steps},
+                           "message_bytes_per_neighbour_per_step": info["message_bytes"], "wall_ms_per_step_max": main["wall_ms_per_step_max"]},
                 "clocks": clk, "gpu_launches": int(cs[3]),
-                "e2e": {"value": n * e2e_steps / float(te[0]), "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h) + 8 * world,
+                "e2e": {"value": n * e2e_steps / e2e_max, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h) + 8 * world,
                         "steps": e2e_steps, "api": "per rank: fishabm_set_state_owned(its fish, pinned host arrays) + halo exchange + fishabm_step(1) + fishabm_get_state_owned + fishabm_sum_quality"},
-                "roofline": {"bound": "fp32", "kernel": "neighbour_kernel_v2", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "roofline": {"bound": "fp32", "kernel": "neighbour_kernel", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp32_peak, "traffic": None, "per": "rank (slowest rank's launch time, mean rank's pairs)",
                              "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock)", "flops_per_launch": flops,
-                             "launch_ms": per_launch_ms, "share_of_step": float(cm[4]) / ms_max},
-                "cpu_baseline": None}
+                             "launch_ms": per_launch_ms, "share_of_step": float(cm[4]) / main["ms_max"]},
+                "per_rank": main["per_rank"],
+                "c4_one_gpu": one_gpu, "efficiency_vs_c4_one_gpu": value / (world * one_gpu["value"]),
+                "parity_spot_check": parity, "transports": transports, "ensemble": ens,
+                "cpu_baseline": None, "build": build_info()}
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -183,6 +183,12 @@ int fishabm_last_pass_stats(fishabm_ctx* ctx, fishabm_pass_stats* out);
 int fishabm_launch_count(const fishabm_ctx* ctx, uint64_t* out);
 /* enable pair counters (small cost) */
 int fishabm_enable_stats(fishabm_ctx* ctx, int32_t on);
+/* phase timing of fishabm_step / fishabm_step_enqueue (off by default: five event records per step).  ms4 = device time
+ * summed over the (first 512) steps of the most recent call, by phase:
+ *   [0] neighbour pass   [1] per-fish update (+ packing / publishing the slab messages)
+ *   [2] slab exchange (waiting for the neighbours' messages; 0 for a whole school)   [3] ingest + counting sort */
+int fishabm_enable_phase_timing(fishabm_ctx* ctx, int32_t on);
+int fishabm_last_phase_ms(const fishabm_ctx* ctx, float* ms4, int32_t* steps);
 
 /* ---- slab decomposition: one school split along x over nranks GPUs, one context per rank ---------------------
  * (no reference counterpart: fish_mod.cpp is single-threaded; BASELINE.json north_star asks for it.)

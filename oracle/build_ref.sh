@@ -5,6 +5,9 @@
 # where it lies under $REF (default /root/reference) and is never copied into the repository:
 # the one-line `#define num` edit is made on a temporary file that is deleted after compiling.
 # Usage: oracle/build_ref.sh [num ...]      (default: 60 200 1000 10000 1000000)
+# REF_OPT / REF_SUFFIX select the optimisation level and a file-name suffix: the parity libraries are -O2; the reference's
+# own build script compiles without -O (fishmod_compile.sh:1), so `REF_OPT=-O0 REF_SUFFIX=_O0 build_ref.sh 60 1000` builds
+# the as-shipped variants bench.py times for the single-thread CPU baseline.
 set -euo pipefail
 here="$(cd "$(dirname "$0")" && pwd)"
 REF="${REF:-/root/reference}"
@@ -12,6 +15,7 @@ out="$here/_ref"
 mkdir -p "$out"
 [ -f "$REF/fish_mod.cpp" ] || { echo "build_ref: $REF/fish_mod.cpp not found (reference absent: keeping prebuilt $out)"; exit 0; }
 nums=("$@"); [ ${#nums[@]} -gt 0 ] || nums=(60 200 1000 10000 1000000)
+opt="${REF_OPT:--O2}"; suffix="${REF_SUFFIX:-}"
 tmp="$(mktemp -d)"; trap 'rm -rf "$tmp"' EXIT
 for n in "${nums[@]}"; do
   # grid stride: the reference hard-codes 250 columns (fish_mod.cpp:24-25); the 1M-fish timing
@@ -22,8 +26,8 @@ for n in "${nums[@]}"; do
       -e "24s/^#define n_cols 250/#define n_cols ${stride}/" \
       -e "25s/^#define n_rows 250/#define n_rows ${stride}/" "$REF/fish_mod.cpp" > "$tu"
   grep -q "^#define num ${n}\$" "$tu" || { echo "build_ref: line 23 of fish_mod.cpp is not '#define num 60'"; exit 1; }
-  g++ -std=c++11 -O2 -ffp-contract=off -fPIC -shared -w -mcmodel=large -I"$here/shim" -I"$here" -DREF_TU="\"$tu\"" \
-      "$here/ref_harness.cpp" -o "$out/libfishref_${n}.so" -lpthread
-  echo "built $out/libfishref_${n}.so"
+  g++ -std=c++11 "$opt" -ffp-contract=off -fPIC -shared -w -mcmodel=large -I"$here/shim" -I"$here" -DREF_TU="\"$tu\"" \
+      "$here/ref_harness.cpp" -o "$out/libfishref_${n}${suffix}.so" -lpthread
+  echo "built $out/libfishref_${n}${suffix}.so"
 done
 cp "$REF/quality.csv" "$out/quality.csv"

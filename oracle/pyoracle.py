@@ -263,14 +263,16 @@ class RefLib:
     _cache: dict = {}
 
     @staticmethod
-    def available(num: int) -> bool:
-        return os.path.exists(os.path.join(REF_DIR, f"libfishref_{num}.so"))
+    def available(num: int, suffix: str = "") -> bool:
+        return os.path.exists(os.path.join(REF_DIR, f"libfishref_{num}{suffix}.so"))
 
-    def __new__(cls, num: int):
-        if num in cls._cache:
-            return cls._cache[num]
+    def __new__(cls, num: int, suffix: str = ""):
+        """suffix "_O0": the same translation unit compiled without optimisation, as the reference ships it
+        (fishmod_compile.sh:1); timing only"""
+        if (num, suffix) in cls._cache:
+            return cls._cache[(num, suffix)]
         self = super().__new__(cls)
-        path = os.path.join(REF_DIR, f"libfishref_{num}.so")
+        path = os.path.join(REF_DIR, f"libfishref_{num}{suffix}.so")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run oracle/build_ref.sh {num} where /root/reference exists")
         L = C.CDLL(path)
@@ -296,7 +298,7 @@ class RefLib:
         self.L = L
         self.num = num
         assert L.ref_num() == num
-        cls._cache[num] = self
+        cls._cache[(num, suffix)] = self
         return self
 
     def set_world(self, w: int, h: int, food_cell: int = 20):
