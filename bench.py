@@ -445,7 +445,8 @@ def ours(args, rank: int, world: int, local_rank: int):
 
     cpu = cpu_baseline_leg(n, w, d) if not args.no_cpu_baseline else None
     S.close()
-    del flush
+    l2_note = "flushed between steps (256 MiB write)" if flush is not None else "state larger than L2"
+    flush = None
     torch.cuda.empty_cache()
     # the 1-GPU base of the C4 scaling curve (the N>1 lines run C4), the small configurations, and configs[4]
     extra = {}
@@ -460,7 +461,7 @@ def ours(args, rank: int, world: int, local_rank: int):
             "scaling_note": "the N=1 line is C3 (1M fish); the N>1 lines are C4 (16.8M fish, strong scaling over 2/4/8 GPUs) whose 1-GPU base "
                             "is c4_one_gpu below (and is re-measured inside every N>1 line)",
             "config": {"workload": workload_string(n, w), "n_fish": n, "world": w,
-                       "l2": "flushed between steps (256 MiB write)" if flush is not None else "state larger than L2",
+                       "l2": l2_note,
                        "timing": "CUDA events on the library's stream around each fishabm_step(1); K steps + the trailing sample pass"},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu, "parity_spot_check": parity, "build": build_info(), **extra}

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "neighbour_v2.cuh"
+#include "neighbour_v3.cuh"
 #include "ensemble.cuh"
 
 using namespace fishk;
@@ -80,7 +81,8 @@ struct fishabm_ctx {
     bool have_state = false;
     bool pending_sample = false;  // sample() of step `step-1` not yet applied (it shares the next move's neighbour pass)
     bool stats_on = false;
-    int nb_variant = 2;  // neighbour kernel design: 2 = candidate-parallel (default), 1 = focal-parallel (FISHABM_NEIGHBOUR=v1)
+    int nb_variant = 3;  // neighbour kernel design: 3 = candidate-parallel, packed-half filter + branch-free pair round (default);
+                         // 2 = candidate-parallel, fp32 filter (FISHABM_NEIGHBOUR=v2); 1 = focal-parallel (FISHABM_NEIGHBOUR=v1)
     uint64_t launches = 0;
     float last_ms = 0.f;
 
@@ -185,6 +187,7 @@ cudaError_t preload_kernels() {
     L((const void*)in_zone_generic_kernel); L((const void*)index_by_id_kernel); L((const void*)ingest_incoming_kernel);
     L((const void*)ingest_kernel); L((const void*)neighbour_kernel<false>); L((const void*)neighbour_kernel<true>);
     L((const void*)neighbour_kernel_v2<false>); L((const void*)neighbour_kernel_v2<true>); L((const void*)scan_finish_kernel);
+    L((const void*)neighbour_kernel_v3<false>); L((const void*)neighbour_kernel_v3<true>);
     L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
     L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
     L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel);
@@ -258,8 +261,13 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         a.split = std::max(1, std::min(32, (2 * ctx->nb_grid * V2_WARPS) / std::max(1, own_cells)));
         if (const char* sp = getenv("FISHABM_SPLIT")) a.split = std::max(1, std::min(32, atoi(sp)));
         const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V2_WARPS));
-        if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
-        else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+        if (ctx->nb_variant == 2) {
+            if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+            else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+        } else {
+            if (ctx->stats_on) neighbour_kernel_v3<true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a);
+            else neighbour_kernel_v3<false><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a);
+        }
     }
     ctx->launches += 1;
     if (timed) CK(cudaEventRecord(e1, ctx->stream));
@@ -679,18 +687,23 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (ok) {
         A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
     }
+    const char* variant = getenv("FISHABM_NEIGHBOUR");
+    if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
+    if (variant && strcmp(variant, "v2") == 0) c->nb_variant = 2;
     if (ok) {
         int per_sm = 0, sms = 0;
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
-        A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
+        static_assert(V2_WARPS == V3_WARPS && V2_THREADS == V3_THREADS, "the work split assumes the same CTA shape");
+        if (c->nb_variant == 2) A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
+        else A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v3<false>, V3_THREADS, V3_SMEM_BYTES));
         c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
         int scan_per_sm = 0;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_per_sm, scan_fused_kernel, SCAN_THREADS, 0));
         c->scan_resident = scan_per_sm * sms / 2;  // the fused scan spins on a flag: only with every block resident, with margin
     }
-    const char* variant = getenv("FISHABM_NEIGHBOUR");
-    if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
     c->h_q8 = (uint8_t*)malloc((size_t)c->qrows * c->qcols > 0 ? (size_t)c->qrows * c->qcols : 1);
     if (!ok || !c->h_q8) {
         std::string msg = "device allocation failed: " + g_create_error;

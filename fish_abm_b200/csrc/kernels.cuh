@@ -350,6 +350,108 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     return unc;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Round form of the pair math (neighbour_kernel_v3, ensemble_kernel): 32 pairs of ONE focal fish, one per lane.
+// The hot path is straight-line, branch-free code: geometry, rounding bands, classification, bearing, weight, sincos.
+// Everything rare -- a borderline predicate (fp64 re-check), a tie draw -- is detected as a flag and, if ANY lane of
+// the round raises it (about 1 round in 2500), the whole round is redone by the generic pair_math above before
+// anything has been accumulated: one warp-uniform branch per round instead of per-lane divergence.  Focal fish with an
+// exotic raw heading (|dir| >= 540) take the generic code for all their rounds (the caller's choice).
+// A lane without a pair is given a candidate beyond every radius (no `live` predicate); a coincident fish (d2 == 0)
+// turns into NaNs that fail every comparison, exactly the reference's NaN drop (fish_mod.cpp:252-254).
+// Sums are kept as RAW float bit patterns (cos + 12.0f as an integer, i.e. value * 2^20 + FIX_MAGIC_BITS) added with
+// 32-bit wrap-around; the bias n_zone * FIX_MAGIC_BITS is removed once per focal fish (pair_sums_unbias), saving two
+// subtractions per pair.
+// Counts.  PACK8 = true : ONE word, n15 | n100 << 8 | n200 << 16 | front << 24 (a reduction covers <= 255 candidates);
+//          PACK8 = false: two words as in PairAcc (16 bits each, <= 1024 candidates per reduction), no tie diagnostic.
+// ------------------------------------------------------------------------------------------------------
+struct PairAccR { unsigned c_far, c_near, ax0, ay0, ax1, ay1, ax2, ay2; };
+__device__ __forceinline__ void pair_acc_clear(PairAccR& A) { A.c_far = A.c_near = 0u; A.ax0 = A.ay0 = A.ax1 = A.ay1 = A.ax2 = A.ay2 = 0u; }
+template <bool PACK8>
+__device__ __forceinline__ int4 unpack_counts_r(unsigned c_far, unsigned c_near) {  // n15, n100, n200, front
+    if (PACK8) return make_int4((int)(c_far & 0xFFu), (int)((c_far >> 8) & 0xFFu), (int)((c_far >> 16) & 0xFFu), (int)(c_far >> 24));
+    return make_int4((int)(c_near >> 16), (int)(c_near & 0xFFFFu), (int)(c_far & 0xFFFFu), (int)((c_far >> 16) & 0x7FFu));
+}
+
+// reduced raw sums r[6] + the counts -> exact integer sums (bias removed); valid while |sum| < 2^31
+__device__ __forceinline__ void pair_sums_unbias(const unsigned* r, const int4& cc, long long* s) {
+    const unsigned b0 = (unsigned)cc.x * (unsigned)FIX_MAGIC_BITS, b1 = (unsigned)(cc.y - cc.x) * (unsigned)FIX_MAGIC_BITS,
+                   b2 = (unsigned)(cc.z - cc.y) * (unsigned)FIX_MAGIC_BITS;
+    s[0] = (long long)(int)(r[0] - b0); s[1] = (long long)(int)(r[1] - b0);
+    s[2] = (long long)(int)(r[2] - b1); s[3] = (long long)(int)(r[3] - b1);
+    s[4] = (long long)(int)(r[4] - b2); s[5] = (long long)(int)(r[5] - b2);
+}
+
+// the generic per-lane code for one round, results folded into the raw accumulators
+template <bool PACK8, class Raw, class Ids>
+__device__ __forceinline__ bool pair_round_generic(bool live, float fx, float fy, float fc, float fs, float fdir, bool exotic, float qx, float qy,
+                                                float qc, float qs, uint64_t seed, uint32_t replicate, uint32_t step_move, const Raw& raw,
+                                                const Ids& ids, PairAccR& A) {
+    PairAcc T;
+    pair_acc_clear(T);
+    const bool rechecked = pair_math(live, fx, fy, fc, fs, fdir, exotic, qx, qy, qc, qs, seed, replicate, step_move, raw, ids, T);
+    const unsigned i15 = (unsigned)T.c_near >> 16, i100 = (unsigned)T.c_near & 0xFFFFu, i200 = (unsigned)T.c_far & 0xFFFFu;
+    const unsigned ifr = ((unsigned)T.c_far >> 16) & 0x7FFu;
+    if (PACK8) A.c_far += i15 | (i100 << 8) | (i200 << 16) | (ifr << 24);
+    else { A.c_far += i200 | (ifr << 16); A.c_near += (unsigned)T.c_near; }
+    A.ax0 += (unsigned)T.ax0 + i15 * (unsigned)FIX_MAGIC_BITS; A.ay0 += (unsigned)T.ay0 + i15 * (unsigned)FIX_MAGIC_BITS;
+    A.ax1 += (unsigned)T.ax1 + (i100 - i15) * (unsigned)FIX_MAGIC_BITS; A.ay1 += (unsigned)T.ay1 + (i100 - i15) * (unsigned)FIX_MAGIC_BITS;
+    A.ax2 += (unsigned)T.ax2 + (i200 - i100) * (unsigned)FIX_MAGIC_BITS; A.ay2 += (unsigned)T.ay2 + (i200 - i100) * (unsigned)FIX_MAGIC_BITS;
+    return rechecked;
+}
+
+// live: the lane holds a pair (only the generic fallback needs to know; the fast path relies on a far-away candidate)
+template <bool PACK8, class Raw, class Ids>
+__device__ __forceinline__ bool pair_round(bool live, float fx, float fy, float fc, float fs, float fdir, float qx, float qy,
+                                           float qc, float qs, uint64_t seed, uint32_t replicate, uint32_t step_move, const Raw& raw,
+                                           const Ids& ids, PairAccR& A) {
+    const float dx = qx - fx, dy = qy - fy;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float dot = fmaf(fc, dx, fs * dy);
+    const float cross = fmaf(fc, dy, -fs * dx);
+    const float rinv = rsqrt_ftz(d2);          // d2 == 0 -> +inf -> d, ca = NaN -> no predicate below holds
+    const float d = d2 * rinv, ca = dot * rinv;
+    // rounding bands (see pair_math)
+    const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
+    const float near_r = fminf(fminf(fabsf(d - 15.f), fabsf(d - 100.f)), fabsf(d - 200.f));
+    const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
+    const bool front = ca > 0.f;
+    const bool unc = near_r < BAND_R || near_c < tb || (fabsf(cross) * rinv < COLLINEAR_BAND && front);
+    const bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F;
+    const bool inter = vis && in200;
+    const bool al = in100 && !in15;
+    // bearing of the neighbour (avoid / attract: of its position; align: of its heading), fish_mod.cpp:316-351
+    const float crossA = fmaf(fc, qs, -fs * qc), dotA = fmaf(fc, qc, fs * qs);
+    const float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
+    const bool tie = (in15 && beta == 0.f) || (al && fabsf(beta) >= PI_F);
+    if (__any_sync(0xFFFFFFFFu, unc || (inter && tie)))   // warp-uniform: redo the round with the generic per-lane code
+        return pair_round_generic<PACK8>(live, fx, fy, fc, fs, fdir, false, qx, qy, qc, qs, seed, replicate, step_move, raw, ids, A);
+    const float t = in15 ? beta - copysignf(PI_F, beta) : beta;
+    const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
+    const float kz = in15 ? 0.1f : 0.004f;
+    const float wgt = rcp_ftz(fmaf(kz * ee, ee, 2.f));
+    const float th = t * wgt;
+    float sn, cs;
+    __sincosf(th, &sn, &cs);
+    const unsigned vx = (unsigned)__float_as_int(cs + FIX_MAGIC), vy = (unsigned)__float_as_int(sn + FIX_MAGIC);
+    if (PACK8) {
+        unsigned inc = in100 ? 0x010100u : 0x010000u;
+        inc = in15 ? 0x010101u : inc;
+        if (inter) A.c_far += inc;
+        if (front && in200) A.c_far += 0x01000000u;
+    } else {
+        if (inter) A.c_far += 1u;
+        if (front && in200) A.c_far += 0x10000u;
+        unsigned near_inc = in100 ? 1u : 0u;
+        near_inc = in15 ? 0x10001u : near_inc;
+        if (inter) A.c_near += near_inc;
+    }
+    if (inter && in15) { A.ax0 += vx; A.ay0 += vy; }
+    if (inter && al) { A.ax1 += vx; A.ay1 += vy; }
+    if (inter && !in100) { A.ax2 += vx; A.ay2 += vy; }
+    return false;
+}
+
 // heading unit vector of a stored heading (degrees, fp32): THE one place it is computed, so that a state that went
 // through get_state / set_state continues bit-identically to one that stayed on the device
 // (a true division: multiplying by a rounded 1/180 would triple the error of the unit vector, which the bearing bands of

@@ -358,15 +358,16 @@ def test_rechecked_pairs_are_rare_and_counted(q100):
     assert st["rechecked"] < 1e-3 * st["candidates"]
 
 
-def test_two_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
-    """the focal-parallel (v1) and candidate-parallel (v2, the default) neighbour kernels accumulate integers, so every
-    output must be identical, whatever the candidate order"""
+def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
+    """the focal-parallel (v1), the candidate-parallel fp32-filter (v2) and the default (v3: packed-half filter, branch-free
+    pair round, raw-bit sums) neighbour kernels accumulate integers from the same per-pair arithmetic, so every output must be
+    identical, whatever the candidate order"""
     n, w = 60_000, 8_000   # ~37 fish per cell on average, some cells above 64
     d = synth.uniform_state(n, w, w, seed=131)
     d["coords"][:5000] = (np.array([4100.0, 4100.0]) + np.random.default_rng(3).uniform(0, 180, (5000, 2))).astype(np.float32)  # a dense clump: >256 candidates
     q = synth.tile_quality(q100, w, w)
     res = []
-    for variant in ("v1", "v2"):
+    for variant in ("v1", "v2", "v3"):
         monkeypatch.setenv("FISHABM_NEIGHBOUR", variant)
         S = School(n=n, w=w, h=w, seed=17)
         S.set_state(**d); S.set_quality(q)
@@ -374,7 +375,7 @@ def test_two_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
         S.step(3)
         res.append((zc, turn, S.get_state(), S.get_quality()))
         S.close()
-    for other in (1,):
+    for other in (1, 2):
         assert np.array_equal(res[0][0], res[other][0])
         assert np.array_equal(res[0][1], res[other][1])
         for k in res[0][2]:
@@ -382,4 +383,4 @@ def test_two_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
         assert np.array_equal(res[0][3], res[other][3])
     O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, q.copy(), seed=17)
     ids = np.r_[np.arange(0, 5000, 97), np.arange(5000, n, 1021)].astype(np.int32)
-    assert np.array_equal(res[1][0][ids], O.zone_counts(ids))
+    assert np.array_equal(res[2][0][ids], O.zone_counts(ids))
