@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfishabm.so")
+LIB_PATH = os.environ.get("FISHABM_LIB") or os.path.join(HERE, "libfishabm.so")   # FISHABM_LIB: a development build to A/B against
 
 OK, E_ARG, E_CUDA, E_STATE, E_NOMEM, E_COMM = 0, -1, -2, -3, -4, -5
 MODE_CELL_FP32, MODE_BRUTE_FP64, MODE_ENSEMBLE = 0, 1, 2

@@ -42,7 +42,13 @@ def nvcc_version() -> str:
         return "unavailable"
 
 
-def build_lib(force: bool = False, verbose: bool = False, extra=()) -> str:
+def build_lib(force: bool = False, verbose: bool = False, extra=(), out: str | None = None) -> str:
+    """out: build a variant (extra flags, e.g. -DFISHABM_V3_MIN_CTAS=3) to another path, for A/B runs with FISHABM_LIB"""
+    if out:
+        cmd = [nvcc_path(), *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-ccbin", shutil.which("g++") or "g++",
+               "-I", os.path.join(HERE, "..", "include"), *extra, *sources(), "-o", out, "-lcudart"]
+        subprocess.run(cmd, check=True)
+        return out
     if not force and not needs_build():
         LAST.update(decision="reused (libfishabm.so newer than every source)", nvcc=None)
         return LIB

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             const float fdir = s_c0[f].x;
             const bool exotic = fabsf(fdir) >= 540.f;
             const int cxf = k1.w / a.ny, cyf = k1.w % a.ny;
-            PairAcc P;
+            PairAccR P;
             pair_acc_clear(P);
             for (int j0 = 0; j0 < n; j0 += 32) {
                 const int j = j0 + lane;
@@ -92,17 +92,19 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
                 if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
                 const bool live = valid && dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
                 if (!__any_sync(FULL, live)) continue;
-                pair_math(
-                    live, F.x, F.y, F.z, F.w, fdir, exotic, Q.x + (float)dcx * CELL_F, Q.y + (float)dcy * CELL_F, Q.z, Q.w, a.seed, replicate,
-                    step_move, [&](float& rx, float& ry, int& kcode) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); },
-                    [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; }, P);
+                // a lane without a pair gets a candidate beyond every radius (pair_round has no `live` predicate)
+                const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + (float)dcy * CELL_F : 3.0e17f;
+                auto raw = [&](float& rx, float& ry, int& kcode) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); };
+                auto ids = [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; };
+                pair_round<false>(live, exotic, F.x, F.y, F.z, F.w, fdir, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
             }
-            const long long sums[6] = {(long long)__reduce_add_sync(FULL, P.ax0), (long long)__reduce_add_sync(FULL, P.ay0),
-                                       (long long)__reduce_add_sync(FULL, P.ax1), (long long)__reduce_add_sync(FULL, P.ay1),
-                                       (long long)__reduce_add_sync(FULL, P.ax2), (long long)__reduce_add_sync(FULL, P.ay2)};
-            const int cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
-            const int4 cc = unpack_counts(cfar, cnear);
-            const int c15 = cc.x, c100 = cc.y, c200 = cc.z, cfr = cc.w, ties = unpack_ties(cfar);
+            const unsigned red[6] = {__reduce_add_sync(FULL, P.ax0), __reduce_add_sync(FULL, P.ay0), __reduce_add_sync(FULL, P.ax1),
+                                     __reduce_add_sync(FULL, P.ay1), __reduce_add_sync(FULL, P.ax2), __reduce_add_sync(FULL, P.ay2)};
+            const unsigned cfar = __reduce_add_sync(FULL, P.c_far), cnear = __reduce_add_sync(FULL, P.c_near);
+            const int4 cc = unpack_counts_r<false>(cfar, cnear);
+            long long sums[6];
+            pair_sums_unbias(red, cc, sums);
+            const int c15 = cc.x, c100 = cc.y, c200 = cc.z, cfr = cc.w, ties = 0;
             if (lane == 0) {
                 const FocalResult r = focal_result(a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,
                                                    c15, c100, c200, cfr, sums, ties);

@@ -402,7 +402,7 @@ __device__ __forceinline__ bool pair_round_generic(bool live, float fx, float fy
 
 // live: the lane holds a pair (only the generic fallback needs to know; the fast path relies on a far-away candidate)
 template <bool PACK8, class Raw, class Ids>
-__device__ __forceinline__ bool pair_round(bool live, float fx, float fy, float fc, float fs, float fdir, float qx, float qy,
+__device__ __forceinline__ bool pair_round(bool live, bool exotic, float fx, float fy, float fc, float fs, float fdir, float qx, float qy,
                                            float qc, float qs, uint64_t seed, uint32_t replicate, uint32_t step_move, const Raw& raw,
                                            const Ids& ids, PairAccR& A) {
     const float dx = qx - fx, dy = qy - fy;
@@ -424,8 +424,9 @@ __device__ __forceinline__ bool pair_round(bool live, float fx, float fy, float 
     const float crossA = fmaf(fc, qs, -fs * qc), dotA = fmaf(fc, qc, fs * qs);
     const float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
     const bool tie = (in15 && beta == 0.f) || (al && fabsf(beta) >= PI_F);
-    if (__any_sync(0xFFFFFFFFu, unc || (inter && tie)))   // warp-uniform: redo the round with the generic per-lane code
-        return pair_round_generic<PACK8>(live, fx, fy, fc, fs, fdir, false, qx, qy, qc, qs, seed, replicate, step_move, raw, ids, A);
+    // warp-uniform: redo the round with the generic per-lane code (`exotic` is the same in every lane: the focal fish's)
+    if (__any_sync(0xFFFFFFFFu, unc || (inter && tie)) || exotic)
+        return pair_round_generic<PACK8>(live, fx, fy, fc, fs, fdir, exotic, qx, qy, qc, qs, seed, replicate, step_move, raw, ids, A);
     const float t = in15 ? beta - copysignf(PI_F, beta) : beta;
     const float ee = d - (in15 ? 0.f : (al ? 15.f : 200.f));
     const float kz = in15 ? 0.1f : 0.004f;

@@ -29,6 +29,9 @@
 
 namespace fishk {
 
+#ifndef FISHABM_V3_MIN_CTAS
+#define FISHABM_V3_MIN_CTAS 4        // resident CTAs per SM the register allocation is held to (4: 64 registers, 32 warps per SM)
+#endif
 constexpr int V3_WARPS = 8;
 constexpr int V3_THREADS = V3_WARPS * 32;
 constexpr int V3_SLOTS = 256;         // window slots (queue entries are bytes); the last one is a permanent far-away candidate
@@ -41,8 +44,11 @@ constexpr float V3_R2H = 2528.f;
 struct V3WarpSmem {
     float4 win[V3_SLOTS];                                  // window candidates in the focal cell's frame: x, y, cos, sin
     uint32_t hx[V3_SLOTS / 2], hy[V3_SLOTS / 2];           // the same coordinates as fp16 pairs: element 32*s + l = candidates (64*s + l, 64*s + 32 + l)
-    long long acc[V3_FMAX][6];                             // multi-batch only: exact cos/sin sums (avoid x,y, align x,y, attract x,y)
-    int4 cnt[V3_FMAX];                                     // multi-batch only: n15, n100, n200, front
+    union {
+        uint32_t res[V3_FMAX][8];                          // one window batch: the reduced raw sums (6) and packed counts of every focal fish
+        long long acc[V3_FMAX][6];                         // several batches: exact cos/sin sums (avoid x,y, align x,y, attract x,y)
+    };
+    int4 cnt[V3_FMAX];                                     // several batches: n15, n100, n200, front
     float4 frec[V3_FMAX];
     float fdir[V3_FMAX];
     int fidx[V3_FMAX];
@@ -65,7 +71,7 @@ __device__ __forceinline__ void v3_setp_lt2(uint32_t a, uint32_t b, bool& plo, b
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const NeighArgs a) {
+__global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_kernel_v3(const NeighArgs a) {
     extern __shared__ __align__(16) unsigned char v3_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -114,28 +120,41 @@ __global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const Neigh
             const int base = b * V3_WIN;
             const int fill = min(T - base, V3_WIN);
             const int padded = (fill + 64) & ~63;   // at least one padding slot; slot V3_SLOTS - 1 is always padding
-            const int p1 = S.run_pre[1], p2 = S.run_pre[2], p3 = S.run_pre[3], p4 = S.run_pre[4];
-            const int p5 = S.run_pre[5], p6 = S.run_pre[6], p7 = S.run_pre[7], p8 = S.run_pre[8];
-            for (int j0 = 0; j0 < padded; j0 += 64) {   // two candidates per lane and iteration: j0 + lane, j0 + 32 + lane
-                float xs[2], ys[2];
+            const float4 far = make_float4(V3_FAR_X, V3_FAR_Y, 1.f, 0.f);
+            // range-major copy: each of the 9 stencil cells is a contiguous run of sorted records, shifted into the focal
+            // cell's frame by a per-cell constant (the periodic minimum image).  Three cells (one stencil row) at a time so
+            // that three loads are in flight; a cell with more than 32 fish in this batch takes the trailing loop.
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {
+                float4 r[3];
+                int u[3], hi[3], src[3];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = j0 + 32 * h + lane;
-                    float4 w = make_float4(V3_FAR_X, V3_FAR_Y, 1.f, 0.f);
-                    if (j < fill) {
-                        const int u = base + j;
-                        const int k = (u >= p1) + (u >= p2) + (u >= p3) + (u >= p4) + (u >= p5) + (u >= p6) + (u >= p7) + (u >= p8);
-                        const float4 r = __ldg(&a.rec[S.run_start[k] + u - S.run_pre[k]]);
-                        const int ky = (k * 11) >> 5, kx = k - 3 * ky;  // k / 3, k % 3 for k < 9
-                        w = make_float4(r.x + (float)(kx - 1) * CELL_F, r.y + (float)(ky - 1) * CELL_F, r.z, r.w);
-                    }
-                    S.win[j] = w;
-                    xs[h] = (w.x - V3_HCENTRE) * V3_HSCALE; ys[h] = (w.y - V3_HCENTRE) * V3_HSCALE;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int k = 3 * ky + kx;
+                    const int pk = S.run_pre[k];
+                    u[kx] = max(pk, base) + lane; hi[kx] = min(S.run_pre[k + 1], base + fill); src[kx] = S.run_start[k] - pk;
+                    if (u[kx] < hi[kx]) r[kx] = __ldg(&a.rec[src[kx] + u[kx]]);
                 }
-                S.hx[(j0 >> 1) + lane] = v3_pack_half2(xs[0], xs[1]);
-                S.hy[(j0 >> 1) + lane] = v3_pack_half2(ys[0], ys[1]);
+                const float sy = (float)(ky - 1) * CELL_F;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float sx = (float)(kx - 1) * CELL_F;
+                    if (u[kx] < hi[kx]) S.win[u[kx] - base] = make_float4(r[kx].x + sx, r[kx].y + sy, r[kx].z, r[kx].w);
+                    for (int v = u[kx] + 32; v < hi[kx]; v += 32) {
+                        const float4 q = __ldg(&a.rec[src[kx] + v]);
+                        S.win[v - base] = make_float4(q.x + sx, q.y + sy, q.z, q.w);
+                    }
+                }
             }
-            if (lane == 0) S.win[V3_SLOTS - 1] = make_float4(V3_FAR_X, V3_FAR_Y, 1.f, 0.f);
+            for (int j = fill + lane; j < padded; j += 32) S.win[j] = far;
+            if (lane == 0) S.win[V3_SLOTS - 1] = far;
+            __syncwarp();
+            // the same coordinates as packed fp16 pairs for the filter: element 32*s + l = candidates (64*s + l, 64*s + 32 + l)
+            for (int j0 = 0; j0 < padded; j0 += 64) {
+                const float2 p = *reinterpret_cast<const float2*>(&S.win[j0 + lane]), q = *reinterpret_cast<const float2*>(&S.win[j0 + 32 + lane]);
+                S.hx[(j0 >> 1) + lane] = v3_pack_half2(fmaf(p.x, V3_HSCALE, -V3_HCENTRE * V3_HSCALE), fmaf(q.x, V3_HSCALE, -V3_HCENTRE * V3_HSCALE));
+                S.hy[(j0 >> 1) + lane] = v3_pack_half2(fmaf(p.y, V3_HSCALE, -V3_HCENTRE * V3_HSCALE), fmaf(q.y, V3_HSCALE, -V3_HCENTRE * V3_HSCALE));
+            }
             __syncwarp();
             staged = b;
             return fill;
@@ -172,8 +191,9 @@ __global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const Neigh
                     const float4 me = a.rec[i];
                     const int slot = nf + __popc(amask & lt_mask);
                     S.frec[slot] = me; S.fdir[slot] = a.cold0[i].x; S.fidx[slot] = i;
-                    S.hfx[slot] = v3_pack_half2((me.x - V3_HCENTRE) * V3_HSCALE, (me.x - V3_HCENTRE) * V3_HSCALE);
-                    S.hfy[slot] = v3_pack_half2((me.y - V3_HCENTRE) * V3_HSCALE, (me.y - V3_HCENTRE) * V3_HSCALE);
+                    const float hxs = fmaf(me.x, V3_HSCALE, -V3_HCENTRE * V3_HSCALE), hys = fmaf(me.y, V3_HSCALE, -V3_HCENTRE * V3_HSCALE);
+                    S.hfx[slot] = v3_pack_half2(hxs, hxs);
+                    S.hfy[slot] = v3_pack_half2(hys, hys);
                 }
                 nf += __popc(amask);
                 pos += take;
@@ -182,9 +202,13 @@ __global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const Neigh
             if (nf == 0) continue;
             if (STATS) st_focal += (unsigned)nf;
 
-            // lane f keeps focal fish f's reduced sums of the current batch in registers; shared-memory accumulators are
-            // only touched when the stencil needs more than one window batch
-            unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, mcw = 0;
+            // the reduced sums of every focal fish go to shared memory (one lane stores them): raw for a single window batch,
+            // unbiased 64-bit running sums when the stencil needs several batches
+            if (nbatch > 1 && lane < nf) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) S.acc[lane][k] = 0;
+                S.cnt[lane] = make_int4(0, 0, 0, 0);
+            }
             for (int b = 0; b < nbatch; ++b) {
                 const int fill = (staged == b) ? min(T - b * V3_WIN, V3_WIN) : stage(b);
                 const int nst = (fill + 63) >> 6;
@@ -229,51 +253,38 @@ __global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const Neigh
                         nb = (uint32_t)a.cold1[src].w;
                         my = (uint32_t)a.cold1[S.fidx[f]].w;
                     };
-                    if (fabsf(fdir) < 540.f) {
-                        const unsigned char* qp = S.queue + lane;
-                        for (int q0 = 0; q0 < qn; q0 += 32, qp += 32) {
-                            const int j = (int)*qp;
-                            const float4 Q = S.win[j];
-                            const bool unc = pair_round<true>(
-                                q0 + lane < qn, F.x, F.y, F.z, F.w, fdir, Q.x, Q.y, Q.z, Q.w, a.seed, a.replicate, a.step_move,
-                                [&](float& rx, float& ry, int& kcode) { raw_of(j, rx, ry, kcode); },
-                                [&](uint32_t& my, uint32_t& nb) { ids_of(j, my, nb); }, P);
-                            if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
-                        }
-                    } else {   // exotic raw heading: the generic code for every round
-                        for (int q0 = 0; q0 < qn; q0 += 32) {
-                            const int j = (int)S.queue[q0 + lane];
-                            const float4 Q = S.win[j];
-                            const bool unc = pair_round_generic<true>(
-                                q0 + lane < qn, F.x, F.y, F.z, F.w, fdir, true, Q.x, Q.y, Q.z, Q.w, a.seed, a.replicate, a.step_move,
-                                [&](float& rx, float& ry, int& kcode) { raw_of(j, rx, ry, kcode); },
-                                [&](uint32_t& my, uint32_t& nb) { ids_of(j, my, nb); }, P);
-                            if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
-                        }
+                    const bool exotic = !(fabsf(fdir) < 540.f);   // exotic raw heading: the generic code for every round
+                    const unsigned char* qp = S.queue + lane;
+                    for (int q0 = 0; q0 < qn; q0 += 32, qp += 32) {
+                        const int j = (int)*qp;
+                        const float4 Q = S.win[j];
+                        const bool unc = pair_round<true>(
+                            q0 + lane < qn, exotic, F.x, F.y, F.z, F.w, fdir, Q.x, Q.y, Q.z, Q.w, a.seed, a.replicate, a.step_move,
+                            [&](float& rx, float& ry, int& kcode) { raw_of(j, rx, ry, kcode); },
+                            [&](uint32_t& my, uint32_t& nb) { ids_of(j, my, nb); }, P);
+                        if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
                     }
-                    // ---- reduce the lanes' partial sums; lane f owns focal fish f's values
+                    // ---- reduce the lanes' partial sums; lane 0 files them under focal fish f
                     const unsigned r0 = __reduce_add_sync(FULL, P.ax0), r1 = __reduce_add_sync(FULL, P.ay0);
                     const unsigned r2 = __reduce_add_sync(FULL, P.ax1), r3 = __reduce_add_sync(FULL, P.ay1);
                     const unsigned r4 = __reduce_add_sync(FULL, P.ax2), r5 = __reduce_add_sync(FULL, P.ay2);
                     const unsigned cw = __reduce_add_sync(FULL, P.c_far);
                     if (STATS) st_inter += (unsigned)((cw >> 16) & 0xFFu);
-                    if (lane == f) { m0 = r0; m1 = r1; m2 = r2; m3 = r3; m4 = r4; m5 = r5; mcw = cw; }
-                }
-                if (nbatch > 1 && lane < nf) {
-                    const unsigned r[6] = {m0, m1, m2, m3, m4, m5};
-                    long long s[6];
-                    const int4 cc = unpack_counts_r<true>(mcw, 0u);
-                    pair_sums_unbias(r, cc, s);
-                    if (b == 0) {
+                    if (lane == 0) {
+                        if (nbatch == 1) {
+                            *reinterpret_cast<uint4*>(&S.res[f][0]) = make_uint4(r0, r1, r2, r3);
+                            *reinterpret_cast<uint4*>(&S.res[f][4]) = make_uint4(r4, r5, cw, 0u);
+                        } else {
+                            const unsigned r[6] = {r0, r1, r2, r3, r4, r5};
+                            long long sm[6];
+                            const int4 cc = unpack_counts_r<true>(cw, 0u);
+                            pair_sums_unbias(r, cc, sm);
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) S.acc[lane][k] = s[k];
-                        S.cnt[lane] = cc;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) S.acc[lane][k] += s[k];
-                        int4 o = S.cnt[lane];
-                        o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
-                        S.cnt[lane] = o;
+                            for (int k = 0; k < 6; ++k) S.acc[f][k] += sm[k];
+                            int4 o = S.cnt[f];
+                            o.x += cc.x; o.y += cc.y; o.z += cc.z; o.w += cc.w;
+                            S.cnt[f] = o;
+                        }
                     }
                 }
             }
@@ -287,9 +298,10 @@ __global__ void __launch_bounds__(V3_THREADS, 4) neighbour_kernel_v3(const Neigh
                     const int4 cc = S.cnt[lane];
                     finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], 0);
                 } else {
-                    const unsigned r[6] = {m0, m1, m2, m3, m4, m5};
+                    const uint4 ra = *reinterpret_cast<const uint4*>(&S.res[lane][0]), rb = *reinterpret_cast<const uint4*>(&S.res[lane][4]);
+                    const unsigned r[6] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y};
                     long long sums[6];
-                    const int4 cc = unpack_counts_r<true>(mcw, 0u);
+                    const int4 cc = unpack_counts_r<true>(rb.z, 0u);
                     pair_sums_unbias(r, cc, sums);
                     finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, sums, 0);
                 }
