@@ -13,12 +13,20 @@ MODE_CELL_FP32, MODE_BRUTE_FP64, MODE_ENSEMBLE = 0, 1, 2
 STREAM_CHOICE, STREAM_ERROR, STREAM_RANDOMWALK, STREAM_QUALITY, STREAM_SEED, STREAM_SAMPLE, STREAM_INIT = range(7)
 
 
+class ModelParams(C.Structure):
+    """fishabm_model_params: the reference's literals as run-time parameters"""
+    _fields_ = [("lag_after_feed", C.c_int32), ("sample_rate_fed", C.c_int32), ("sample_rate_unfed", C.c_int32),
+                ("sample_draw_max", C.c_int32), ("error_range", C.c_int32), ("randomwalk_range", C.c_int32),
+                ("alone_align_min", C.c_int32), ("reserved", C.c_int32), ("fed_speed_factor", C.c_double),
+                ("weight_align", C.c_double), ("weight_attract", C.c_double)]
+
+
 class Params(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
                 ("mode", C.c_int32), ("device", C.c_int32), ("replicates", C.c_int32), ("rolling", C.c_int32),
                 ("seed", C.c_uint64), ("speed_norm", C.c_double), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("n_global", C.c_int32), ("capacity", C.c_int32), ("halo_capacity", C.c_int32),
-                ("migrant_capacity", C.c_int32), ("replicate0", C.c_uint32), ("force_slab", C.c_int32)]
+                ("migrant_capacity", C.c_int32), ("replicate0", C.c_uint32), ("force_slab", C.c_int32), ("model", ModelParams)]
 
 
 class SlabInfo(C.Structure):
@@ -51,6 +59,7 @@ SYMBOLS = [
     "fishabm_slab_buffers", "fishabm_slab_end_step", "fishabm_slab_copy", "fishabm_slab_get_endpoint",
     "fishabm_slab_attach", "fishabm_step_enqueue", "fishabm_wait", "fishabm_set_state_owned", "fishabm_get_state_owned",
     "fishabm_create_environment", "fishabm_check_fp64", "fishabm_enable_phase_timing", "fishabm_last_phase_ms",
+    "fishabm_model_params_default", "fishabm_set_replicate_models",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -67,6 +76,8 @@ def load():
     L = C.CDLL(LIB_PATH)
     vp, i32, u32, dbl = C.c_void_p, C.c_int32, C.c_uint32, C.c_double
     L.fishabm_params_default.argtypes = [C.POINTER(Params)]
+    L.fishabm_model_params_default.argtypes = [C.POINTER(ModelParams)]
+    L.fishabm_set_replicate_models.argtypes = [vp, C.POINTER(ModelParams), i32]
     L.fishabm_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     L.fishabm_destroy.argtypes = [vp]
     L.fishabm_destroy.restype = None

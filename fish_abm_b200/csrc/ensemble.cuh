@@ -33,6 +33,7 @@ struct EnsembleArgs {
     int* intake;      // [rows][R][n] or null
     int intake_every;
     int4* cnt; float* turn; uint32_t* aux;  // [R][n] outputs of ENS_OP_QUERY
+    const Model* models;  // [R]: every replicate has its own model constants (parameter sweeps, BASELINE.json configs[4])
 };
 
 __host__ __device__ inline size_t ensemble_smem_bytes(int n, int qcells) {
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
 
     const int rep = blockIdx.x;
     const uint32_t replicate = a.replicate0 + (uint32_t)rep;
+    __shared__ Model model;   // this replicate's model constants
+    if (tid == 0) model = a.models[rep];
     const size_t base = (size_t)rep * n;
     for (int i = tid; i < n; i += ENS_THREADS) { s_rec[i] = a.rec[base + i]; s_c0[i] = a.cold0[base + i]; s_c1[i] = a.cold1[base + i]; }
     const uint8_t* gq = a.quality + (size_t)rep * a.qcells;
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             pair_sums_unbias(red, cc, sums);
             const int c15 = cc.x, c100 = cc.y, c200 = cc.z, cfr = cc.w, ties = 0;
             if (lane == 0) {
-                const FocalResult r = focal_result(a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,
+                const FocalResult r = focal_result(model, a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,
                                                    c15, c100, c200, cfr, sums, ties);
                 s_cnt[f] = r.cnt; s_turn[f] = r.turn; s_aux[f] = r.aux;
             }
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             s_updq[i] = -1;
             if (do_sample) {  // sample(), fish_mod.cpp:546-556
                 if (aux & AUX_WANTS) {
-                    c1.x = 10;
+                    c1.x = model.lag_after_feed;
                     // feed(), fish_mod.cpp:560-574: feeders of one food cell are served lowest id first
                     const uint32_t key = aux & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS);
                     int rank = 0, total = 0;
@@ -138,14 +141,14 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
                     const int gy = (c1.w % a.ny) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
                     const int qi = gy * a.qcols + gx;
                     const int q = (int)s_q[qi];
-                    if (rank < q) { c0.z = 0.5f; c1.z += 1; c1.y = 30; atomicSub(s_total, 1); }
-                    else c1.y = 0;
+                    if (rank < q) { c0.z = model.fed_sf; c1.z += 1; c1.y = model.rate_fed; atomicSub(s_total, 1); }
+                    else c1.y = model.rate_unfed;
                     if (rank == 0 && q > 0) { s_updq[i] = qi; s_updv[i] = q - min(q, total); }  // written after every feeder has read
                 } else if (c1.x == 0) c1.y += 1;
                 else c1.x -= 1;
             }
             if (do_move) {  // move(), fish_mod.cpp:165-179
-                const int err = fishrng::draw(a.seed, replicate, step_move, (uint32_t)i, STREAM_ERROR, 0, -10, 10);
+                const int err = fishrng::draw(a.seed, replicate, step_move, (uint32_t)i, STREAM_ERROR, 0, -model.error_range, model.error_range);
                 float4 r = s_rec[i];
                 int cx = c1.w / a.ny, cy = c1.w % a.ny;
                 const bool moving = c1.x == 0;

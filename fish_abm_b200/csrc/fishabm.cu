@@ -77,6 +77,8 @@ struct fishabm_ctx {
     std::vector<int> h_ids;
     std::vector<char> h_tmp;
     double speed_norm = 1.0;
+    Model model;                 // the context's model constants in device form
+    Model* d_models = nullptr;   // ensembles: one per replicate
     uint32_t step = 0;
     bool have_state = false;
     bool pending_sample = false;  // sample() of step `step-1` not yet applied (it shares the next move's neighbour pass)
@@ -130,6 +132,31 @@ int fail(fishabm_ctx* c, int code, const char* fmt, ...) {
 template <class T> cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 1); }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void model_defaults(fishabm_model_params* m) {
+    memset(m, 0, sizeof *m);
+    m->lag_after_feed = 10; m->sample_rate_fed = 30; m->sample_rate_unfed = 0; m->sample_draw_max = 35;
+    m->error_range = 10; m->randomwalk_range = 45; m->alone_align_min = 5;
+    m->fed_speed_factor = 0.5; m->weight_align = 1.7; m->weight_attract = 1.7 - 1;   // (1.7 - i), fish_mod.cpp:385-386
+}
+const char* model_invalid(const fishabm_model_params& m) {
+    if (m.lag_after_feed < 0 || m.lag_after_feed > (1 << 20)) return "lag_after_feed must be in [0, 2^20]";
+    if (m.sample_rate_fed < 0 || m.sample_rate_unfed < 0 || m.sample_rate_fed > (1 << 20) || m.sample_rate_unfed > (1 << 20)) return "sample rates must be in [0, 2^20]";
+    if (m.sample_draw_max < 0 || m.sample_draw_max > (1 << 20)) return "sample_draw_max must be in [0, 2^20]";
+    if (m.error_range < 0 || m.error_range > 180 || m.randomwalk_range < 0 || m.randomwalk_range > 180) return "error_range / randomwalk_range must be in [0, 180] degrees";
+    if (m.alone_align_min < 0) return "alone_align_min must be >= 0";
+    if (!(m.fed_speed_factor >= 0.0 && m.fed_speed_factor <= 3.0)) return "fed_speed_factor must be in [0, 3]";
+    if (!(m.weight_align >= 0.0 && m.weight_attract >= 0.0 && m.weight_align + m.weight_attract > 0.0)) return "combination weights must be >= 0 and not both zero";
+    return nullptr;
+}
+Model to_device_model(const fishabm_model_params& m) {
+    Model d;
+    d.lag_after_feed = m.lag_after_feed; d.rate_fed = m.sample_rate_fed; d.rate_unfed = m.sample_rate_unfed;
+    d.sample_draw_max = m.sample_draw_max; d.error_range = m.error_range; d.randomwalk_range = m.randomwalk_range;
+    d.alone_align_min = m.alone_align_min; d.pad = 0;
+    d.fed_sf = (float)m.fed_speed_factor; d.w_align = (float)m.weight_align; d.w_attract = (float)m.weight_attract; d.pad2 = 0.f;
+    return d;
+}
 
 // ---- NCCL, loaded on demand (only slab contexts that call fishabm_slab_connect need it).  The handful of
 // declarations below restate the public NCCL 2.x C API so that building the library does not need nccl.h.
@@ -234,6 +261,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = ctx->p.replicate0;
     a.split = 1;
+    a.model = ctx->model;
     a.work_counter = ctx->work_counter + ctx->wc_parity;            // the persistent kernel's two cell counters alternate:
     a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
     if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -320,6 +348,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.do_sample = do_sample; u.do_move = do_move; u.rolling = ctx->p.rolling;
     u.step_move = step_move; u.seed = ctx->p.seed; u.replicate = ctx->p.replicate0; u.speed_norm_inv2 = (float)(2.0 / ctx->speed_norm);
     u.slab = ctx->slab ? 1 : 0;
+    u.model = ctx->model;
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
     u.part = UPD_ALL;
@@ -507,6 +536,7 @@ EnsembleArgs ens_args(fishabm_ctx* c, int op, int nsteps) {
     a.op = op; a.nsteps = nsteps; a.step0 = c->step;
     a.rolling = c->p.rolling; a.seed = c->p.seed; a.speed_norm = c->speed_norm;
     a.cnt = c->cnt; a.turn = c->turn; a.aux = c->aux;
+    a.models = c->d_models;
     return a;
 }
 int ens_launch(fishabm_ctx* ctx, const EnsembleArgs& a) {
@@ -559,6 +589,13 @@ int fishabm_params_default(fishabm_params* p) {
     p->speed_norm = 0.0;
     p->rank = 0; p->nranks = 1; p->n_global = 0; p->capacity = 0;
     p->halo_capacity = 0; p->migrant_capacity = 0; p->force_slab = 0;
+    model_defaults(&p->model);
+    return 0;
+}
+
+int fishabm_model_params_default(fishabm_model_params* m) {
+    if (!m) return FISHABM_E_ARG;
+    model_defaults(m);
     return 0;
 }
 
@@ -574,6 +611,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         return fail(nullptr, FISHABM_E_ARG, "w and h must be multiples of 200 and at least 600 (got %d x %d)", p->w, p->h);
     if (p->mode != FISHABM_MODE_CELL_FP32 && p->mode != FISHABM_MODE_ENSEMBLE) return fail(nullptr, FISHABM_E_ARG, "mode %d is not available in this build", p->mode);
     if (p->replicates < 1) return fail(nullptr, FISHABM_E_ARG, "replicates must be >= 1");
+    if (const char* why = model_invalid(p->model)) return fail(nullptr, FISHABM_E_ARG, "fishabm_params.model: %s", why);
     const bool ens = p->replicates > 1 || p->mode == FISHABM_MODE_ENSEMBLE;
     if (ens && (p->n > ENS_MAX_FISH || p->nranks != 1 || p->force_slab))
         return fail(nullptr, FISHABM_E_ARG, "ensembles need n <= %d fish per school and no slabs (replicates shard across GPUs by replicate0)", ENS_MAX_FISH);
@@ -616,6 +654,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     c->ncell = g.ncell;
     c->qrows = p->h / FOOD_I; c->qcols = c->own * FOOD_PER_CELL; c->qcols_g = p->w / FOOD_I; c->qcol0 = c->col0 * FOOD_PER_CELL;
     c->speed_norm = p->speed_norm > 0 ? p->speed_norm : (double)p->n;
+    c->model = to_device_model(p->model);
     if (c->slab) {
         const double per_col = (double)p->n / nx_g;
         c->cap_g = p->halo_capacity > 0 ? p->halo_capacity : (int)(2.0 * per_col) + 4096;
@@ -657,6 +696,11 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->upd_count, 2)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
     A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 2)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
     A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R)); A(dalloc(&c->scan_sync, 2));
+    A(dalloc(&c->d_models, (size_t)c->R));
+    if (ok) {
+        std::vector<Model> hm((size_t)c->R, c->model);
+        A(cudaMemcpy(c->d_models, hm.data(), hm.size() * sizeof(Model), cudaMemcpyHostToDevice));
+    }
     if (ok) A(cudaMemset(c->scan_sync, 0, 2 * sizeof(int)));
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
@@ -726,7 +770,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
-    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums); cudaFree(c->scan_sync);
+    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums); cudaFree(c->scan_sync); cudaFree(c->d_models);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
     cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);
@@ -948,7 +992,7 @@ int fishabm_initialize(fishabm_ctx* ctx, double speed) {
         const uint32_t rep = ctx->p.replicate0 + (uint32_t)r;
         for (int f = 0; f < ctx->n; ++f) {
             const size_t i = (size_t)r * ctx->n + f;
-            dir[i] = (double)fishrng::draw(ctx->p.seed, rep, 0, (uint32_t)f, STREAM_RANDOMWALK, 0, -45, 45);
+            dir[i] = (double)fishrng::draw(ctx->p.seed, rep, 0, (uint32_t)f, STREAM_RANDOMWALK, 0, -45, 45);   // distrib_randomwalk as the reference declares it (:30,196)
             coords[2 * i] = ctx->p.w / 2 + fishrng::draw(ctx->p.seed, rep, 0, (uint32_t)f, STREAM_INIT, 0, 0, 200) - 100;
             coords[2 * i + 1] = ctx->p.h / 2 + fishrng::draw(ctx->p.seed, rep, 1, (uint32_t)f, STREAM_INIT, 0, 0, 200) - 100;
         }
@@ -1170,7 +1214,7 @@ int fishabm_check_fp64(fishabm_ctx* ctx, const int32_t* ids, int32_t k, int32_t*
     CK(cudaMemsetAsync(ctx->pos_of_id, 0xFF, (size_t)ctx->n * sizeof(int), s));
     index_by_id_kernel<<<cdiv(ctx->cap, 256), 256, 0, s>>>(b.cold1, ctx->cell_start, ctx->g, ctx->pos_of_id);
     CheckArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->pos_of_id, ctx->st_ids, k, ctx->st_i4, ctx->st_dir, ctx->st_lag,
-                ctx->n, ctx->g, ctx->p.w, ctx->p.h, ctx->step, ctx->p.seed, ctx->p.replicate0};
+                ctx->n, ctx->g, ctx->p.w, ctx->p.h, ctx->step, ctx->p.seed, ctx->p.replicate0, ctx->model};
     check_fp64_kernel<<<cdiv(k * 32, 256), 256, 0, s>>>(a);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -1317,7 +1361,7 @@ int fishabm_feed(fishabm_ctx* ctx, const int32_t* ids, int32_t k) {
     CK(cudaMemcpyAsync(ctx->st_lag, ids, (size_t)k * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->pos_of_id, 0xFF, (size_t)ctx->n * sizeof(int), ctx->stream));
     index_by_id_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(b.cold1, ctx->cell_start, ctx->g, ctx->pos_of_id);
-    FeedArgs a{b.cold0, b.cold1, b.rec, b.cell, ctx->st_lag, k, ctx->quality, ctx->n, ctx->qcols, ctx->g, ctx->pos_of_id};
+    FeedArgs a{b.cold0, b.cold1, b.rec, b.cell, ctx->st_lag, k, ctx->quality, ctx->n, ctx->qcols, ctx->g, ctx->pos_of_id, ctx->model};
     feed_list_kernel<<<1, 32, 0, ctx->stream>>>(a);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -1471,6 +1515,25 @@ int fishabm_slab_copy(void* dst, const void* src, int64_t bytes) {
     if (!dst || !src || bytes < 0) return FISHABM_E_ARG;
     if (cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault) != cudaSuccess) return FISHABM_E_CUDA;
     if (cudaDeviceSynchronize() != cudaSuccess) return FISHABM_E_CUDA;  // device-to-device copies return early
+    return 0;
+}
+
+int fishabm_set_replicate_models(fishabm_ctx* ctx, const fishabm_model_params* models, int32_t count) {
+    if (!ctx || !models) return fail(ctx, FISHABM_E_ARG, "fishabm_set_replicate_models: null argument");
+    if (count != ctx->R) return fail(ctx, FISHABM_E_ARG, "fishabm_set_replicate_models: %d models for %d replicates", count, ctx->R);
+    if (ctx->step_open) return fail(ctx, FISHABM_E_STATE, "a slab step is open: call fishabm_slab_end_step first");
+    std::vector<Model> hm;
+    try { hm.resize((size_t)count); } catch (...) { return fail(ctx, FISHABM_E_NOMEM, "out of host memory"); }
+    for (int r = 0; r < count; ++r) {
+        if (const char* why = model_invalid(models[r])) return fail(ctx, FISHABM_E_ARG, "fishabm_set_replicate_models: model %d: %s", r, why);
+        hm[(size_t)r] = to_device_model(models[r]);
+    }
+    CK(cudaSetDevice(ctx->p.device));
+    if (ctx->have_state) { int rc = flush_pending(ctx); if (rc) return rc; }   // the pending sample() belongs to the old constants
+    CK(cudaMemcpyAsync(ctx->d_models, hm.data(), hm.size() * sizeof(Model), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->model = hm[0];
+    ctx->p.model = models[0];
     return 0;
 }
 

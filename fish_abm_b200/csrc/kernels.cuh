@@ -60,6 +60,23 @@ struct Grid {
     int nx_g;              // global columns (W/200)
 };
 
+// the model constants the reference writes as literals, as run-time parameters (include/fishabm.h: fishabm_model_params);
+// the defaults are the reference's values
+struct Model {
+    int lag_after_feed;      // 10,  fish_mod.cpp:548
+    int rate_fed;            // 30,  :570
+    int rate_unfed;          // 0,   :573
+    int sample_draw_max;     // 35,  :33  distrib_sample(0, 35)
+    int error_range;         // 10,  :29  distrib_error(-10, 10)
+    int randomwalk_range;    // 45,  :30  distrib_randomwalk(-45, 45)
+    int alone_align_min;     // 5,   :546 alone = no avoid-zone neighbour and fewer than 5 align-zone neighbours
+    int pad;
+    float fed_sf;            // 0.5, :566
+    float w_align;           // 1.7, :385-386 (1.7 - i, i = 0)
+    float w_attract;         // 0.7  (1.7 - i, i = 1)
+    float pad2;
+};
+
 struct NeighArgs {
     const float4* rec;
     const float4* cold0;
@@ -79,6 +96,7 @@ struct NeighArgs {
                                  // the resident warps, up to 32 for small or dense schools that would otherwise leave SMs idle
     int* work_counter;           // work-item dispenser of the persistent (v2) kernel, zero at launch
     int* work_counter_next;      // the other dispenser: cleared by this launch for the next one
+    Model model;
 };
 
 // aux bits
@@ -210,7 +228,7 @@ __device__ __forceinline__ float average_from_sums_f(long long x, long long y) {
 // averageturn (:379-408), the random walk (:372-374) and sample()'s feeding decision (:543-547).
 // s[6] = fixed-point cos/sin sums (avoid x,y; align x,y; attract x,y), exact integers.
 struct FocalResult { int4 cnt; float turn; uint32_t aux; };
-__device__ __forceinline__ FocalResult focal_result(uint64_t seed, uint32_t replicate, uint32_t step_sample, uint32_t step_move, int do_sample,
+__device__ __forceinline__ FocalResult focal_result(const Model& m, uint64_t seed, uint32_t replicate, uint32_t step_sample, uint32_t step_move, int do_sample,
                                                     uint32_t id, int lag, int sample_rate, float fx, float fy, int n15, int n100, int n200,
                                                     int nfr, const long long* s, int ties) {
     uint32_t aux = AUX_EVALUATED;
@@ -223,18 +241,18 @@ __device__ __forceinline__ FocalResult focal_result(uint64_t seed, uint32_t repl
         float sa, ca, st, ct;
         __sincosf(aa, &sa, &ca);
         __sincosf(tt, &st, &ct);
-        const float xs = fmaf(1.7f, ca, 0.7f * ct), ys = fmaf(1.7f, sa, 0.7f * st);
+        const float xs = fmaf(m.w_align, ca, m.w_attract * ct), ys = fmaf(m.w_align, sa, m.w_attract * st);
         turn = (ys == 0.f) ? (xs >= 0.f ? 0.f : 180.f) : atan2_fast(ys, xs) * (180.f / PI_F);
     } else if (n_al > 0) turn = average_from_sums_f(s[2], s[3]);
     else if (n_at > 0) turn = average_from_sums_f(s[4], s[5]);
     else {
-        turn = (float)fishrng::draw(seed, replicate, step_move, id, STREAM_RANDOMWALK, 0, -45, 45);
+        turn = (float)fishrng::draw(seed, replicate, step_move, id, STREAM_RANDOMWALK, 0, -m.randomwalk_range, m.randomwalk_range);
         aux |= AUX_RANDOMWALK;
     }
     aux |= (uint32_t)min(ties, 127) << AUX_TIE_SHIFT;
     if (do_sample && lag == 0) {  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
-        const int dr = fishrng::draw(seed, replicate, step_sample, id, STREAM_SAMPLE, 0, 0, 35);
-        const bool alone = (n_av == 0 && n_al < 5);
+        const int dr = fishrng::draw(seed, replicate, step_sample, id, STREAM_SAMPLE, 0, 0, m.sample_draw_max);
+        const bool alone = (n_av == 0 && n_al < m.alone_align_min);
         if (sample_rate > dr && !alone) {
             const int fxl = min((int)fx / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)fy / FOOD_I, FOOD_PER_CELL - 1);
             aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
@@ -247,7 +265,7 @@ __device__ __forceinline__ FocalResult focal_result(uint64_t seed, uint32_t repl
 
 __device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k1, float fx, float fy, int n15, int n100, int n200,
                                              int nfr, const long long* s, int ties) {
-    const FocalResult r = focal_result(a.seed, a.replicate, a.step_sample, a.step_move, a.do_sample, (uint32_t)k1.w, k1.x, k1.y, fx, fy,
+    const FocalResult r = focal_result(a.model, a.seed, a.replicate, a.step_sample, a.step_move, a.do_sample, (uint32_t)k1.w, k1.x, k1.y, fx, fy,
                                        n15, n100, n200, nfr, s, ties);
     a.cnt[idx] = r.cnt;
     a.turn[idx] = r.turn;
@@ -719,6 +737,7 @@ struct UpdateArgs {
     int slab;           // pack migrants / ghosts for the two neighbours
     SlabMsg out_left, out_right;
     int part;           // UPD_ALL, or (slabs, peer-memory transport) UPD_EDGES first and UPD_MIDDLE after the publish
+    Model model;
 };
 // A fish moves less than one cell per step, so only the two outermost owned columns on each side can produce
 // migrants or ghosts: updating them FIRST lets the messages leave (slab_publish_kernel) while the bulk of the slab is
@@ -770,7 +789,7 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
 
     if (a.do_sample) {  // sample(), fish_mod.cpp:546-556
         if (aux & AUX_WANTS) {
-            c1.x = 10;
+            c1.x = a.model.lag_after_feed;
             // feed(), fish_mod.cpp:560-574.  Fish that feed on the same food cell in the same step are served in
             // id order (the reference's loop order, :541): rank = feeders of this food cell with a lower id.
             const uint32_t key = aux & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS);
@@ -788,8 +807,8 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
             const int gy = (mycell % ny) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
             const int qi = gy * a.qcols + gx;
             const int q = (int)a.quality[qi];
-            if (rank < q) { c0.z = 0.5f; c1.z += 1; c1.y = 30; }
-            else c1.y = 0;
+            if (rank < q) { c0.z = a.model.fed_sf; c1.z += 1; c1.y = a.model.rate_fed; }
+            else c1.y = a.model.rate_unfed;
             if (rank == 0 && q > 0) {  // the grid itself is only written after every feeder has read it
                 const int k = atomicAdd(a.upd_count, 1);
                 a.upd_idx[k] = qi;
@@ -800,7 +819,7 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
     }
 
     if (a.do_move) {  // move(), fish_mod.cpp:165-179
-        const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -10, 10);
+        const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -a.model.error_range, a.model.error_range);
         float4 r = a.rec[i];
         int cx = mycell / ny, cy = mycell % ny;
         const bool moving = c1.x == 0;
@@ -1226,6 +1245,7 @@ struct CheckArgs {
     int* counts4; double* turn; int* flags;
     int n; Grid g; int w, h;
     uint32_t step; uint64_t seed; uint32_t replicate;
+    Model model;
 };
 enum { CHECK_RANDOMWALK = 1, CHECK_TIES = 2, CHECK_KNIFE = 4 };
 
@@ -1327,12 +1347,12 @@ __global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
     if (n_av > 0) turn = check_averageturn(avx, avy, n_av);             // :356-358
     else if (n_al > 0 && n_at > 0) {                                    // :360-365: weights 1.7 / 0.7
         const double A = check_averageturn(alx, aly, n_al), T = check_averageturn(atx, aty, n_at);
-        const double xs = cos(A * M_PI / 180.0) * 1.7 + cos(T * M_PI / 180.0) * 0.7;
-        const double ys = sin(A * M_PI / 180.0) * 1.7 + sin(T * M_PI / 180.0) * 0.7;
+        const double xs = cos(A * M_PI / 180.0) * (double)a.model.w_align + cos(T * M_PI / 180.0) * (double)a.model.w_attract;
+        const double ys = sin(A * M_PI / 180.0) * (double)a.model.w_align + sin(T * M_PI / 180.0) * (double)a.model.w_attract;
         turn = check_averageturn(xs, ys, 2);
     } else if (n_al > 0) turn = check_averageturn(alx, aly, n_al);
     else if (n_at > 0) turn = check_averageturn(atx, aty, n_at);
-    else { turn = (double)fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_RANDOMWALK, 0, -45, 45); fl |= CHECK_RANDOMWALK; }  // :372-374
+    else { turn = (double)fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_RANDOMWALK, 0, -a.model.randomwalk_range, a.model.randomwalk_range); fl |= CHECK_RANDOMWALK; }  // :372-374
     a.counts4[4 * warp] = c15; a.counts4[4 * warp + 1] = c100; a.counts4[4 * warp + 2] = c200; a.counts4[4 * warp + 3] = cf;
     a.turn[warp] = turn;
     a.flags[warp] = fl;
@@ -1350,6 +1370,7 @@ __global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long lon
 struct FeedArgs {
     float4* cold0; int4* cold1; const float4* rec; const int* cell; const int* ids; int k;
     uint8_t* quality; int n_global, qcols; Grid g; int* pos_of_id;
+    Model model;
 };
 __global__ void index_by_id_kernel(const int4* cold1, const int* cell_start, Grid g, int* pos_of_id) {
     const int i = cell_start[g.own_c0] + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1370,8 +1391,8 @@ __global__ void feed_list_kernel(const FeedArgs a) {
         const int q = a.quality[qi];
         float4 c0 = a.cold0[i];
         int4 c1 = a.cold1[i];
-        if (q > 0) { c0.z = 0.5f; a.quality[qi] = (uint8_t)(q - 1); c1.z += 1; c1.y = 30; }
-        else c1.y = 0;
+        if (q > 0) { c0.z = a.model.fed_sf; a.quality[qi] = (uint8_t)(q - 1); c1.z += 1; c1.y = a.model.rate_fed; }
+        else c1.y = a.model.rate_unfed;
         a.cold0[i] = c0; a.cold1[i] = c1;
     }
 }

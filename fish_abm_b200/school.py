@@ -26,7 +26,7 @@ class School:
     def __init__(self, n: int = 60, w: int = 2000, h: int = 2000, seed: int = 0, device: int = 0,
                  rolling: bool = True, speed_norm: float = 0.0, mode: int = _lib.MODE_CELL_FP32,
                  rank: int = 0, nranks: int = 1, force_slab: bool = False, capacity: int = 0, halo_capacity: int = 0,
-                 migrant_capacity: int = 0, replicates: int = 1, replicate0: int = 0):
+                 migrant_capacity: int = 0, replicates: int = 1, replicate0: int = 0, model: dict | None = None):
         """rank / nranks > 1: this context is one x-slab of the school (see include/fishabm.h and slab.py); n, w, h and
         every array passed in or out still describe the WHOLE school.
         replicates > 1 (or mode=MODE_ENSEMBLE): an ensemble of independent schools; arrays are flat, replicates*n
@@ -38,6 +38,10 @@ class School:
         p.rank, p.nranks, p.force_slab = rank, nranks, int(force_slab)
         p.capacity, p.halo_capacity, p.migrant_capacity = capacity, halo_capacity, migrant_capacity
         p.replicates, p.replicate0 = replicates, replicate0
+        for k, v in (model or {}).items():   # fishabm_model_params: the reference's literals as run-time parameters
+            if not hasattr(p.model, k):
+                raise KeyError(f"unknown model parameter {k!r}")
+            setattr(p.model, k, v)
         self.replicates = replicates
         self.is_slab = nranks > 1 or force_slab
         self.params = p
@@ -125,6 +129,18 @@ class School:
     def initialize(self, speed: float = 5.0):
         """initialize(fish, num, 2, speed, struc), fish_mod.cpp:116,183-206"""
         self._ck(self.L.fishabm_initialize(self.ctx, float(speed)))
+
+    def set_models(self, models):
+        """one dict of model parameters per replicate (missing keys keep the reference's values); a single school takes a
+        list of one.  include/fishabm.h: fishabm_set_replicate_models"""
+        arr = (_lib.ModelParams * len(models))()
+        for m, over in zip(arr, models):
+            self.L.fishabm_model_params_default(C.byref(m))
+            for k, v in over.items():
+                if not hasattr(m, k):
+                    raise KeyError(f"unknown model parameter {k!r}")
+                setattr(m, k, v)
+        self._ck(self.L.fishabm_set_replicate_models(self.ctx, arr, len(models)))
 
     # ---- food grid -----------------------------------------------------------------------------------------
     def set_quality(self, q):
@@ -322,6 +338,16 @@ class Ensemble(School):
     def get_state(self) -> dict:
         g = super().get_state()
         return {k: v.reshape(self.replicates, self.n, *v.shape[1:]) for k, v in g.items()}
+
+    SWEEP = {"sample_rate_fed": (15, 30, 45), "fed_speed_factor": (0.25, 0.5, 0.75)}
+
+    def sweep_default(self) -> str:
+        """BASELINE.json configs[4]: replicate r gets sample_rate_fed = SWEEP[..][(r // 8) % 3] and fed_speed_factor =
+        SWEEP[..][(r // 24) % 3] (the speed sweep itself is per-fish state: speed = 2.5..20 by r % 8)"""
+        r = np.arange(self.replicates) + int(self.params.replicate0)
+        self.set_models([{"sample_rate_fed": self.SWEEP["sample_rate_fed"][(k // 8) % 3],
+                          "fed_speed_factor": self.SWEEP["fed_speed_factor"][(k // 24) % 3]} for k in r])
+        return "speed 2.5..20 (8) x sample_rate_fed 15/30/45 x fed_speed_factor 0.25/0.5/0.75, one combination per replicate"
 
     def zone_counts(self):
         return super().zone_counts().reshape(self.replicates, self.n, 4)

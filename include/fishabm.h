@@ -16,10 +16,11 @@
  *   - calls are synchronous with respect to the host;
  *   - there is no CPU fallback: without a CUDA device fishabm_create fails with FISHABM_E_CUDA.
  *
- * Fixed model constants (literals in the reference): zone radii 15/100/200 (fish_mod.cpp:273-275,543-545),
- * social field of view 330 deg and front cone 180 deg (:167,589), lag 10 (:548), sample_rate 30/0
- * (:570,573), distributions choice(0,1) error(-10,10) randomwalk(-45,45) sample(0,35) (:28-33),
- * food cell 20 units (:56), fed speed_factor 0.5 (:566), combination weights 1.7/0.7 (:385-386).
+ * Model constants.  Geometry is fixed: zone radii 15/100/200 (fish_mod.cpp:273-275,543-545; 200 is the neighbour cell),
+ * social field of view 330 deg and front cone 180 deg (:167,589), food cell 20 units (:56), tie draw choice(0,1) (:28).
+ * Everything else the reference writes as a literal is a run-time parameter with the reference's value as default
+ * (fishabm_model_params): lag 10 (:548), sample_rate 30/0 (:570,573), distributions error(-10,10) randomwalk(-45,45)
+ * sample(0,35) (:29-33), the "alone" threshold 5 (:546), fed speed_factor 0.5 (:566), combination weights 1.7/0.7 (:385-386).
  */
 #ifndef FISHABM_H
 #define FISHABM_H
@@ -57,6 +58,23 @@ enum {
 
 typedef struct fishabm_ctx fishabm_ctx;
 
+/* the behavioural constants of move() / sample() / feed() (literals in the reference; defaults = its values).  One set per
+ * context; an ensemble may give every replicate its own (fishabm_set_replicate_models: parameter sweeps). */
+typedef struct fishabm_model_params {
+    int32_t lag_after_feed;     /* 10   handling time after a feeding attempt, fish_mod.cpp:548 */
+    int32_t sample_rate_fed;    /* 30   sample_rate after a successful feed(), :570 */
+    int32_t sample_rate_unfed;  /* 0    sample_rate after an unsuccessful feed(), :573 */
+    int32_t sample_draw_max;    /* 35   distrib_sample(0, 35), :33: a fish samples when sample_rate > draw */
+    int32_t error_range;        /* 10   distrib_error(-10, 10), :29 (degrees added to every turn) */
+    int32_t randomwalk_range;   /* 45   distrib_randomwalk(-45, 45), :30 (turn of a fish that sees nobody; initial headings) */
+    int32_t alone_align_min;    /* 5    a fish with no avoid-zone neighbour and fewer than 5 align-zone neighbours is "alone"
+                                        and does not sample, :546 */
+    int32_t reserved;
+    double fed_speed_factor;    /* 0.5  speed_factor after a successful feed(), :566 */
+    double weight_align;        /* 1.7  averageturn's comb_weight for the alignment turn, :385-386 (1.7 - i, i = 0) */
+    double weight_attract;      /* 0.7  ... and for the attraction turn (1.7 - i, i = 1) */
+} fishabm_model_params;
+
 typedef struct fishabm_params {
     int32_t struct_size;   /* sizeof(fishabm_params), set by fishabm_params_default */
     int32_t n;             /* fish per school            (#define num / inds.n, fish_mod.cpp:23,37) */
@@ -84,6 +102,7 @@ typedef struct fishabm_params {
                               across GPUs, or one school of it run alone, draws the same numbers */
     int32_t force_slab;    /* 1 = use halo columns and the message path even with nranks == 1 (the slab is then its own
                               neighbour); for testing the decomposition on one GPU */
+    fishabm_model_params model;  /* set to the reference's values by fishabm_params_default */
 } fishabm_params;
 
 /* pair counters of the most recent neighbour pass (for the roofline accounting) */
@@ -95,6 +114,10 @@ typedef struct fishabm_pass_stats {
 } fishabm_pass_stats;
 
 int fishabm_params_default(fishabm_params* p);
+int fishabm_model_params_default(fishabm_model_params* m);
+/* ensembles: one model per replicate (count == replicates), e.g. a sweep of sample_rate_fed x fed_speed_factor x speed;
+ * single schools: count == 1 replaces the context's model.  Takes effect from the next pass; completes a pending sample() first. */
+int fishabm_set_replicate_models(fishabm_ctx* ctx, const fishabm_model_params* models, int32_t count);
 int fishabm_create(const fishabm_params* p, fishabm_ctx** out);
 void fishabm_destroy(fishabm_ctx* ctx);
 /* message of the last failing call on ctx (ctx == NULL: last fishabm_create failure on this thread) */

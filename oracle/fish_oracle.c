@@ -30,6 +30,21 @@
 #endif
 #include "orc_rng.h"
 
+/* the reference's literals as parameters (defaults = the reference's values; the product's fishabm_model_params) */
+typedef struct {
+    int lag_after_feed;   /* 10, fish_mod.cpp:548 */
+    int rate_fed;         /* 30, :570 */
+    int rate_unfed;       /* 0,  :573 */
+    int sample_draw_max;  /* 35, :33 */
+    int error_range;      /* 10, :29 */
+    int randomwalk_range; /* 45, :30 */
+    int alone_align_min;  /* 5,  :546 */
+    int pad;
+    double fed_sf;        /* 0.5, :566 */
+    double w_align;       /* 1.7, :385-386 (1.7 - i, i = 0) */
+    double w_attract;     /* 1.7 - 1 */
+} orc_model;
+
 typedef struct {
     int n;             /* fish (inds.n) */
     int w, h;          /* Structure.w / .h, ints as in fish_mod.cpp:58-59 */
@@ -47,7 +62,13 @@ typedef struct {
     int* sample_rate;
     int* food_intake;
     int* quality; /* [rows][q_stride] */
+    orc_model m;
 } orc_school;
+
+void orc_model_default(orc_model* m) {
+    m->lag_after_feed = 10; m->rate_fed = 30; m->rate_unfed = 0; m->sample_draw_max = 35; m->error_range = 10;
+    m->randomwalk_range = 45; m->alone_align_min = 5; m->pad = 0; m->fed_sf = 0.5; m->w_align = 1.7; m->w_attract = 1.7 - 1;
+}
 
 /* ---- scalar helpers ----------------------------------------------------------------------- */
 
@@ -209,11 +230,15 @@ void orc_social(const orc_school* S, int id, int fov, uint32_t step, orc_social_
     int rw = 0;
     if (n_av > 0) turn = averageturn_sums(av_x, av_y, n_av); /* :356-358 */
     else if (n_al > 0 && n_at > 0) {                          /* :360-365 */
-        double two[2] = {averageturn_sums(al_x, al_y, n_al), averageturn_sums(at_x, at_y, n_at)};
-        turn = orc_averageturn(two, 2, 1);
+        /* averageturn(comb_al_at, 1), :362-365: weights (1.7 - i) for i = 0, 1 = w_align, w_attract */
+        double a0 = averageturn_sums(al_x, al_y, n_al), a1 = averageturn_sums(at_x, at_y, n_at);
+        double xs = 0, ys = 0;
+        xs = xs + cos(a0 * M_PI / 180) * S->m.w_align; ys = ys + sin(a0 * M_PI / 180) * S->m.w_align;
+        xs = xs + cos(a1 * M_PI / 180) * S->m.w_attract; ys = ys + sin(a1 * M_PI / 180) * S->m.w_attract;
+        turn = averageturn_sums(xs, ys, 2);
     } else if (n_al > 0) turn = averageturn_sums(al_x, al_y, n_al);
     else if (n_at > 0) turn = averageturn_sums(at_x, at_y, n_at);
-    else { turn = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_RANDOMWALK, -45, 45); rw = 1; } /* :372-374 */
+    else { turn = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_RANDOMWALK, -S->m.randomwalk_range, S->m.randomwalk_range); rw = 1; } /* :372-374 */
     out->turn = turn; out->n_avoid = n_av; out->n_align = n_al; out->n_attract = n_at;
     out->n_ties = ties; out->randomwalk = rw; out->knife = knife;
 }
@@ -225,12 +250,12 @@ void orc_feed(orc_school* S, int id) {
     int x = (int)S->coords[2 * id], y = (int)S->coords[2 * id + 1];
     int* cell = &S->quality[(size_t)(y / (S->h / S->rows)) * S->q_stride + x / (S->w / S->cols)];
     if (*cell > 0) {
-        S->speed_factor[id] = 0.5;
+        S->speed_factor[id] = S->m.fed_sf;
         *cell = *cell - 1;
         S->food_intake[id] = S->food_intake[id] + 1;
-        S->sample_rate[id] = 30;
+        S->sample_rate[id] = S->m.rate_fed;
     } else {
-        S->sample_rate[id] = 0;
+        S->sample_rate[id] = S->m.rate_unfed;
     }
 }
 
@@ -242,10 +267,10 @@ void orc_sample(orc_school* S, uint32_t step, const int* counts_or_null) {
         int n_avoid, n_align;
         if (counts_or_null) { n_avoid = counts_or_null[4 * id]; n_align = counts_or_null[4 * id + 1] - n_avoid; }
         else { n_avoid = orc_in_zone(S, id, 330, 15); n_align = orc_in_zone(S, id, 330, 100) - n_avoid; }
-        int alone = (n_avoid == 0 && n_align < 5);
+        int alone = (n_avoid == 0 && n_align < S->m.alone_align_min);
         if (S->lag[id] == 0 &&
-            S->sample_rate[id] > orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_SAMPLE, 0, 35) && alone == 0) {
-            S->lag[id] = 10;
+            S->sample_rate[id] > orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_SAMPLE, 0, S->m.sample_draw_max) && alone == 0) {
+            S->lag[id] = S->m.lag_after_feed;
             orc_feed(S, id);
         } else if (S->lag[id] == 0) {
             S->sample_rate[id] = S->sample_rate[id] + 1;
@@ -293,7 +318,7 @@ long orc_sum_quality(const orc_school* S) {
 /* move, fish_mod.cpp:163-181, the reference's sequential in-place loop */
 void orc_move_seq(orc_school* S, uint32_t step) {
     for (int id = 0; id < S->n; ++id) {
-        int err = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_ERROR, -10, 10);
+        int err = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_ERROR, -S->m.error_range, S->m.error_range);
         if (S->lag[id] == 0) {
             double dir = orc_correctangle(S->dir[id]);
             orc_social_out so;
@@ -323,7 +348,7 @@ void orc_move_sync(orc_school* S, uint32_t step, const double* turn_or_null, con
     double* nf = (double*)malloc(sizeof(double) * n);
 #pragma omp parallel for schedule(dynamic, 16)
     for (int id = 0; id < n; ++id) {
-        int err = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_ERROR, -10, 10);
+        int err = orc_draw(S->seed, S->replicate, step, id, ORC_STREAM_ERROR, -S->m.error_range, S->m.error_range);
         nc[2 * id] = S->coords[2 * id]; nc[2 * id + 1] = S->coords[2 * id + 1];
         nf[id] = S->speed_factor[id];
         if (S->lag[id] == 0) {

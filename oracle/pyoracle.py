@@ -59,13 +59,29 @@ class State:
         return self
 
 
+class OrcModel(C.Structure):
+    """orc_model: the reference's literals as parameters (defaults = the reference's values)"""
+    _fields_ = [("lag_after_feed", C.c_int), ("rate_fed", C.c_int), ("rate_unfed", C.c_int), ("sample_draw_max", C.c_int),
+                ("error_range", C.c_int), ("randomwalk_range", C.c_int), ("alone_align_min", C.c_int), ("pad", C.c_int),
+                ("fed_sf", C.c_double), ("w_align", C.c_double), ("w_attract", C.c_double)]
+
+    @staticmethod
+    def default(**over) -> "OrcModel":
+        m = OrcModel(10, 30, 0, 35, 10, 45, 5, 0, 0.5, 1.7, 1.7 - 1)
+        names = {"sample_rate_fed": "rate_fed", "sample_rate_unfed": "rate_unfed", "fed_speed_factor": "fed_sf",
+                 "weight_align": "w_align", "weight_attract": "w_attract"}   # the product's field names are accepted too
+        for k, v in over.items():
+            setattr(m, names.get(k, k), v)
+        return m
+
+
 class _OrcSchool(C.Structure):
     _fields_ = [("n", C.c_int), ("w", C.c_int), ("h", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
                 ("q_stride", C.c_int), ("speed_norm", C.c_double), ("seed", C.c_uint64),
                 ("replicate", C.c_uint32), ("pad_", C.c_uint32),
                 ("coords", C.c_void_p), ("dir", C.c_void_p), ("speed", C.c_void_p),
                 ("speed_factor", C.c_void_p), ("lag", C.c_void_p), ("sample_rate", C.c_void_p),
-                ("food_intake", C.c_void_p), ("quality", C.c_void_p)]
+                ("food_intake", C.c_void_p), ("quality", C.c_void_p), ("m", OrcModel)]
 
 
 class _SocialOut(C.Structure):
@@ -114,7 +130,7 @@ class Oracle:
         return cls._lib
 
     def __init__(self, state: State, w: int = 2000, h: int = 2000, quality: np.ndarray | None = None,
-                 food_cell: int = 20, seed: int = 0, replicate: int = 0, speed_norm: float | None = None):
+                 food_cell: int = 20, seed: int = 0, replicate: int = 0, speed_norm: float | None = None, model: dict | None = None):
         self.L = self.lib()
         self.state = state.normalise()
         self.w, self.h = int(w), int(h)
@@ -125,6 +141,7 @@ class Oracle:
         assert self.quality.shape == (rows, cols), (self.quality.shape, rows, cols)
         self.seed, self.replicate = int(seed), int(replicate)
         self.speed_norm = float(state.n if speed_norm is None else speed_norm)
+        self.model = OrcModel.default(**(model or {}))
 
     def _s(self) -> _OrcSchool:
         st = self.state
@@ -132,7 +149,7 @@ class Oracle:
         return _OrcSchool(st.n, self.w, self.h, rows, cols, cols, self.speed_norm, self.seed, self.replicate, 0,
                           st.coords.ctypes.data, st.dir.ctypes.data, st.speed.ctypes.data,
                           st.speed_factor.ctypes.data, st.lag.ctypes.data, st.sample_rate.ctypes.data,
-                          st.food_intake.ctypes.data, self.quality.ctypes.data)
+                          st.food_intake.ctypes.data, self.quality.ctypes.data, self.model)
 
     # ---- frozen-state queries
     def in_zone(self, fov: int, r: float) -> np.ndarray:

@@ -103,3 +103,23 @@ def test_draw_matches_oracle_addressing(golden):
     """fishabm_draw is pure host arithmetic on the context's seed; compare with the oracle's table without a device
     by calling the same inline code through a context-free path is not possible, so this runs in the gpu suite."""
     assert "lemire" in golden
+
+
+def test_params_struct_matches_the_header_and_defaults_are_the_reference(tmp_path):
+    """the ctypes mirror of fishabm_params (incl. the model block) has the header's size and offsets, and
+    fishabm_params_default fills the reference's literals (fish_mod.cpp:28-33,385-386,546-548,566-573); no device needed"""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fishabm.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(fishabm_params),'
+                   ' offsetof(fishabm_params, model), sizeof(fishabm_model_params), offsetof(fishabm_model_params, fed_speed_factor));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.Params), _lib.Params.model.offset, C.sizeof(_lib.ModelParams), _lib.ModelParams.fed_speed_factor.offset]
+    L = _lib.load()
+    p = _lib.Params()
+    assert L.fishabm_params_default(C.byref(p)) == 0 and p.struct_size == C.sizeof(_lib.Params)
+    m = p.model
+    assert (m.lag_after_feed, m.sample_rate_fed, m.sample_rate_unfed, m.sample_draw_max, m.error_range, m.randomwalk_range,
+            m.alone_align_min) == (10, 30, 0, 35, 10, 45, 5)
+    assert (m.fed_speed_factor, m.weight_align, m.weight_attract) == (0.5, 1.7, 1.7 - 1)
