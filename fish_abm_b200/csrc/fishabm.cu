@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
+
 #include "kernels.cuh"
 #include "neighbour_v2.cuh"
 #include "neighbour_v3.cuh"
@@ -25,6 +27,13 @@ using namespace fishk;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range around each phase of a step: K4 neighbour pass, K5 update (+ message packing), the slab
+// exchange, K1-K3 ingest + counting sort; visible in Nsight Systems / Compute timelines
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Buffers {  // one set of cell-sorted arrays
     float4* rec = nullptr;
@@ -217,7 +226,7 @@ cudaError_t preload_kernels() {
     L((const void*)neighbour_kernel_v3<false>); L((const void*)neighbour_kernel_v3<true>);
     L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
     L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
-    L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel);
+    L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel); L((const void*)brute_fp64_pass_kernel);
     return e;
 }
 
@@ -229,6 +238,7 @@ size_t inbox_flag_off(const fishabm_ctx* c, int side, int slot) { return 4 * c->
 
 // ---- the counting sort: counts (already accumulated in cell_count) -> cell_start; scatter cur -> other
 int rebuild(fishabm_ctx* ctx) {
+    NvtxRange nv("fishabm: K2 scan + K3 scatter (counting sort)");
     const int ntiles = cdiv(ctx->ncell, SCAN_TILE);
     if (ntiles <= ctx->scan_resident) {  // every tile's block is resident at once: one launch
         ScanFusedArgs f{ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start, ctx->scan_sync, ctx->scan_sync + 1, ++ctx->scan_epoch, ntiles};
@@ -253,6 +263,7 @@ enum { PASS_COUNTS = 1, PASS_TURN = 2 };
 
 // K4: one neighbour pass.  active_lag_max < 0 evaluates every fish (frozen-state queries).
 int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_t step_sample, uint32_t step_move, bool timed) {
+    NvtxRange nv("fishabm: K4 neighbour pass");
     const Buffers& b = ctx->buf[ctx->cur];
     NeighArgs a;
     a.rec = b.rec; a.cold0 = b.cold0; a.cold1 = b.cold1; a.cell_start = ctx->cell_start;
@@ -279,7 +290,14 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         CK(cudaEventRecord(e0, ctx->stream));
     }
     const int own_cells = ctx->g.own_c1 - ctx->g.own_c0;
-    if (ctx->nb_variant == 1) {
+    if (ctx->p.mode == FISHABM_MODE_BRUTE_FP64) {
+        BrutePassArgs ba;
+        ba.c = CheckArgs{b.rec, b.cold0, b.cold1, b.cell, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                         ctx->n, ctx->g, ctx->p.w, ctx->p.h, step_move, ctx->p.seed, ctx->p.replicate0, ctx->model};
+        ba.cnt = ctx->cnt; ba.turn = ctx->turn; ba.aux = ctx->aux;
+        ba.active_lag_max = active_lag_max; ba.do_sample = do_sample ? 1 : 0; ba.step_sample = step_sample;
+        brute_fp64_pass_kernel<<<cdiv(ctx->n * 32, 256), 256, 0, ctx->stream>>>(ba);
+    } else if (ctx->nb_variant == 1) {
         const int grid = cdiv(own_cells, NB_WARPS);
         if (ctx->stats_on) neighbour_kernel<true><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
@@ -336,6 +354,7 @@ int publish(fishabm_ctx* ctx) {
 
 // K5 (+ deferred food-grid writes); a move also packs the slab messages
 int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
+    NvtxRange nv("fishabm: K5 update (sample / feed / move, slab message packing)");
     const Buffers& b = ctx->buf[ctx->cur];
     UpdateArgs u;
     u.rec = b.rec; u.cold0 = b.cold0; u.cold1 = b.cold1; u.cell = b.cell; u.cell_start = ctx->cell_start;
@@ -377,6 +396,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
 // after a move: (slab) take in the two received messages, then re-sort
 int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_right) {
     if (ctx->slab) {
+        NvtxRange nv("fishabm: K1 ingest of received slab messages");
         const Buffers& b = ctx->buf[ctx->cur];
         IncomingArgs a{msg(ctx, in_left), msg(ctx, in_right), b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count,
                        ctx->cell_start, ctx->n_unsorted, ctx->err, ctx->cap, ctx->g};
@@ -389,6 +409,7 @@ int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_righ
 
 // the exchange the library drives itself: a lone slab is its own neighbour on both sides; several slabs use NCCL
 int exchange(fishabm_ctx* ctx, unsigned char** in_left, unsigned char** in_right) {
+    NvtxRange nv("fishabm: slab exchange (halo columns + migrants)");
     if (ctx->p.nranks == 1) { *in_left = ctx->out_right; *in_right = ctx->out_left; return 0; }
     if (ctx->p2p) {
         if (!ctx->published) { int rc = publish(ctx); if (rc) return rc; }  // (move() published after its edge columns)
@@ -609,7 +630,10 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (p->n < 1 || p->n >= (1 << 28)) return fail(nullptr, FISHABM_E_ARG, "n must be in [1, 2^28)");
     if (p->w % CELL_I || p->h % CELL_I || p->w < 3 * CELL_I || p->h < 3 * CELL_I)
         return fail(nullptr, FISHABM_E_ARG, "w and h must be multiples of 200 and at least 600 (got %d x %d)", p->w, p->h);
-    if (p->mode != FISHABM_MODE_CELL_FP32 && p->mode != FISHABM_MODE_ENSEMBLE) return fail(nullptr, FISHABM_E_ARG, "mode %d is not available in this build", p->mode);
+    if (p->mode != FISHABM_MODE_CELL_FP32 && p->mode != FISHABM_MODE_ENSEMBLE && p->mode != FISHABM_MODE_BRUTE_FP64)
+        return fail(nullptr, FISHABM_E_ARG, "unknown mode %d", p->mode);
+    if (p->mode == FISHABM_MODE_BRUTE_FP64 && (p->n > 65536 || p->nranks != 1 || p->force_slab || p->replicates != 1))
+        return fail(nullptr, FISHABM_E_ARG, "FISHABM_MODE_BRUTE_FP64 (fp64 all-pairs neighbour pass, O(n^2)) is for one whole school of n <= 65536 fish");
     if (p->replicates < 1) return fail(nullptr, FISHABM_E_ARG, "replicates must be >= 1");
     if (const char* why = model_invalid(p->model)) return fail(nullptr, FISHABM_E_ARG, "fishabm_params.model: %s", why);
     const bool ens = p->replicates > 1 || p->mode == FISHABM_MODE_ENSEMBLE;

@@ -228,6 +228,16 @@ __device__ __forceinline__ float average_from_sums_f(long long x, long long y) {
 // averageturn (:379-408), the random walk (:372-374) and sample()'s feeding decision (:543-547).
 // s[6] = fixed-point cos/sin sums (avoid x,y; align x,y; attract x,y), exact integers.
 struct FocalResult { int4 cnt; float turn; uint32_t aux; };
+// sample()'s decision for one fish (fish_mod.cpp:543-547): AUX_WANTS + the food cell inside its neighbour cell, or 0
+__device__ __forceinline__ uint32_t sample_decision(const Model& m, uint64_t seed, uint32_t replicate, uint32_t step_sample, uint32_t id, int lag,
+                                                    int sample_rate, float fx, float fy, int n_av, int n_al) {
+    if (lag != 0) return 0u;  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
+    const int dr = fishrng::draw(seed, replicate, step_sample, id, STREAM_SAMPLE, 0, 0, m.sample_draw_max);
+    const bool alone = (n_av == 0 && n_al < m.alone_align_min);
+    if (!(sample_rate > dr && !alone)) return 0u;
+    const int fxl = min((int)fx / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)fy / FOOD_I, FOOD_PER_CELL - 1);
+    return AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
+}
 __device__ __forceinline__ FocalResult focal_result(const Model& m, uint64_t seed, uint32_t replicate, uint32_t step_sample, uint32_t step_move, int do_sample,
                                                     uint32_t id, int lag, int sample_rate, float fx, float fy, int n15, int n100, int n200,
                                                     int nfr, const long long* s, int ties) {
@@ -250,14 +260,7 @@ __device__ __forceinline__ FocalResult focal_result(const Model& m, uint64_t see
         aux |= AUX_RANDOMWALK;
     }
     aux |= (uint32_t)min(ties, 127) << AUX_TIE_SHIFT;
-    if (do_sample && lag == 0) {  // the draw is only consumed when lag == 0 (fish_mod.cpp:547)
-        const int dr = fishrng::draw(seed, replicate, step_sample, id, STREAM_SAMPLE, 0, 0, m.sample_draw_max);
-        const bool alone = (n_av == 0 && n_al < m.alone_align_min);
-        if (sample_rate > dr && !alone) {
-            const int fxl = min((int)fx / FOOD_I, FOOD_PER_CELL - 1), fyl = min((int)fy / FOOD_I, FOOD_PER_CELL - 1);
-            aux |= AUX_WANTS | ((uint32_t)(fyl * FOOD_PER_CELL + fxl) << AUX_FOOD_SHIFT);
-        }
-    }
+    if (do_sample) aux |= sample_decision(m, seed, replicate, step_sample, id, lag, sample_rate, fx, fy, n_av, n_al);
     FocalResult r;
     r.cnt = make_int4(n15, n100, n200, nfr); r.turn = turn; r.aux = aux;
     return r;
@@ -1278,12 +1281,10 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= a.k) return;
-    const int id = a.ids[warp];
-    const int fi = (id >= 0 && id < a.n) ? a.pos_of_id[id] : -1;
-    if (fi < 0) { if (lane == 0) { a.turn[warp] = nan(""); a.flags[warp] = -1; for (int q = 0; q < 4; ++q) a.counts4[4 * warp + q] = -1; } return; }
+// the fp64 brute-force evaluation of ONE focal fish (sorted index fi, global id `id`) by one warp: every lane returns the
+// reduced counts, the turn and the flags
+struct CheckOut { int c15, c100, c200, cf; double turn; int flags; };
+__device__ __forceinline__ CheckOut check_eval(const CheckArgs& a, int fi, int id, int lane) {
     const int ny = a.g.ny;
     auto world = [&](int i, double& X, double& Y) {  // exact: cell * 200 + fp32 offset
         const float4 r = a.rec[i];
@@ -1340,7 +1341,6 @@ __global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
     c200 = __reduce_add_sync(0xFFFFFFFFu, c200); cf = __reduce_add_sync(0xFFFFFFFFu, cf);
     ties = __reduce_add_sync(0xFFFFFFFFu, ties); knife = __reduce_add_sync(0xFFFFFFFFu, knife);
     avx = warp_sum(avx); avy = warp_sum(avy); alx = warp_sum(alx); aly = warp_sum(aly); atx = warp_sum(atx); aty = warp_sum(aty);
-    if (lane != 0) return;
     const int n_av = c15, n_al = c100 - c15, n_at = c200 - c100;
     double turn;
     int fl = (ties ? CHECK_TIES : 0) | (knife ? CHECK_KNIFE : 0);
@@ -1353,9 +1353,47 @@ __global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
     } else if (n_al > 0) turn = check_averageturn(alx, aly, n_al);
     else if (n_at > 0) turn = check_averageturn(atx, aty, n_at);
     else { turn = (double)fishrng::draw(a.seed, a.replicate, a.step, (uint32_t)id, STREAM_RANDOMWALK, 0, -a.model.randomwalk_range, a.model.randomwalk_range); fl |= CHECK_RANDOMWALK; }  // :372-374
-    a.counts4[4 * warp] = c15; a.counts4[4 * warp + 1] = c100; a.counts4[4 * warp + 2] = c200; a.counts4[4 * warp + 3] = cf;
-    a.turn[warp] = turn;
-    a.flags[warp] = fl;
+    CheckOut o;
+    o.c15 = c15; o.c100 = c100; o.c200 = c200; o.cf = cf; o.turn = turn; o.flags = fl;
+    return o;
+}
+
+__global__ void __launch_bounds__(256) check_fp64_kernel(const CheckArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.k) return;
+    const int id = a.ids[warp];
+    const int fi = (id >= 0 && id < a.n) ? a.pos_of_id[id] : -1;
+    if (fi < 0) { if (lane == 0) { a.turn[warp] = nan(""); a.flags[warp] = -1; for (int q = 0; q < 4; ++q) a.counts4[4 * warp + q] = -1; } return; }
+    const CheckOut o = check_eval(a, fi, id, lane);
+    if (lane != 0) return;
+    a.counts4[4 * warp] = o.c15; a.counts4[4 * warp + 1] = o.c100; a.counts4[4 * warp + 2] = o.c200; a.counts4[4 * warp + 3] = o.cf;
+    a.turn[warp] = o.turn;
+    a.flags[warp] = o.flags;
+}
+
+// FISHABM_MODE_BRUTE_FP64: the neighbour pass of a whole (small) school as the fp64 brute-force evaluation above -- a warp
+// per fish, every other fish a candidate, no cell list, no fp32 pair arithmetic -- writing the same per-pass outputs
+// (cnt / turn / aux, sorted order) the update kernel consumes.  O(n^2); the "fp64 check mode" of BASELINE.json north_star
+// as a stepping mode.
+struct BrutePassArgs {
+    CheckArgs c;             // c.step = the move's step (tie / random-walk draws); ids / pos_of_id / counts4 / turn / flags unused
+    int4* cnt; float* turn; uint32_t* aux;
+    int active_lag_max, do_sample;
+    uint32_t step_sample;
+};
+__global__ void __launch_bounds__(256) brute_fp64_pass_kernel(const BrutePassArgs a) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= a.c.n) return;
+    const int4 k1 = a.c.cold1[i];
+    if (!(a.active_lag_max < 0 || k1.x <= a.active_lag_max)) { if (lane == 0) a.aux[i] = 0u; return; }
+    const CheckOut o = check_eval(a.c, i, k1.w, lane);
+    if (lane != 0) return;
+    uint32_t aux = AUX_EVALUATED | ((o.flags & CHECK_RANDOMWALK) ? AUX_RANDOMWALK : 0u);
+    const float4 r = a.c.rec[i];
+    if (a.do_sample) aux |= sample_decision(a.c.model, a.c.seed, a.c.replicate, a.step_sample, (uint32_t)k1.w, k1.x, k1.y, r.x, r.y, o.c15, o.c100 - o.c15);
+    a.cnt[i] = make_int4(o.c15, o.c100, o.c200, o.cf);
+    a.turn[i] = (float)o.turn;
+    a.aux[i] = aux;
 }
 
 __global__ void sum_quality_kernel(const uint8_t* q, size_t n, unsigned long long* out) {

@@ -45,7 +45,9 @@ enum {
 enum {
     FISHABM_MODE_CELL_FP32 = 0,  /* product path: cell list + fused fp32 neighbour kernel with fp64 re-check
                                     of borderline predicates */
-    FISHABM_MODE_BRUTE_FP64 = 1, /* not a context mode: the fp64 brute-force evaluator is the call fishabm_check_fp64 */
+    FISHABM_MODE_BRUTE_FP64 = 1, /* fp64 check mode as a stepping mode: every neighbour pass is the brute-force, double-precision
+                                    evaluation of fishabm_check_fp64 over ALL pairs (no cell list, no fp32 pair arithmetic);
+                                    O(n^2), one whole school of n <= 65536 fish.  State and move arithmetic stay fp32. */
     FISHABM_MODE_ENSEMBLE = 2    /* replicate ensemble: one CTA per school, all pairs in shared memory; implied by
                                     replicates > 1, may be forced for a single school (n <= 1024) */
 };

@@ -62,3 +62,32 @@ def test_check_mode_limits(q100):
         S.set_state(**d)
         c, t, f = S.check_fp64([3, 499, 777])      # an id outside the school is marked, not an error
         assert f[2] == -1 and np.isnan(t[2]) and (c[2] == -1).all() and f[0] >= 0
+
+
+def test_brute_fp64_mode_steps_like_the_product_path(q100):
+    """FISHABM_MODE_BRUTE_FP64: every neighbour pass is the fp64 all-pairs evaluation.  Its counts are the product path's
+    (bit-exact), its turns within 1e-5 rad, and a few steps of it keep every integer field identical to the cell-list path
+    (continuous state re-aligned each step so that a rounding difference cannot flip a later decision)."""
+    from fish_abm_b200 import FishAbmError, School, _lib, synth
+    n, w = 3000, 2000
+    d = synth.uniform_state(n, w, w, seed=404)
+    with School(n=n, w=w, h=w, seed=12, mode=_lib.MODE_BRUTE_FP64) as B, School(n=n, w=w, h=w, seed=12) as S:
+        for X in (B, S):
+            X.set_state(**d); X.set_quality(q100)
+        assert np.array_equal(B.zone_counts(), S.zone_counts())
+        tb, ts = B.social()[0], S.social()[0]
+        cc, ct, cf = S.check_fp64(np.arange(n, dtype=np.int32))
+        ok = (cf & 6) == 0
+        assert np.abs(np.deg2rad(tb - ts))[ok].max() < 1e-5
+        assert np.abs(np.deg2rad(tb - ct))[ok].max() < 1e-6      # the mode IS the check evaluation (fp32 only at the output)
+        for step in range(5):
+            B.step(1); S.step(1)
+            gb, gs = B.get_state(), S.get_state()
+            for k in ("lag", "sample_rate", "food_intake"):
+                assert np.array_equal(gb[k], gs[k]), (step, k)
+            assert np.array_equal(B.get_quality(), S.get_quality())
+            assert np.abs(np.deg2rad(gb["dir"] - gs["dir"]))[ok].max() < 1e-5
+            B.set_state(**gs)
+            B.step_index = S.step_index
+    with pytest.raises(FishAbmError):
+        School(n=100_000, w=8000, h=8000, mode=_lib.MODE_BRUTE_FP64)

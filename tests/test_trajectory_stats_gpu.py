@@ -63,3 +63,33 @@ def test_individual_uptake_after_5000_steps(q100):
     h = np.array(st["hist_breaks_0_80_4"], float) / st["fish"]
     hr = np.array(ref["hist_breaks_0_80_4"], float) / (ref["replicates"] * ref["fish"])
     assert np.abs(h - hr).sum() < 0.25  # total-variation style distance between the two uptake histograms
+
+
+def test_speed_factor_histogram_vs_sequential_reference_semantics(q100):
+    """north_star's "speed histogram": the distribution of speed_factor (0.5 right after feeding, else 1 + 2 * front / num,
+    fish_mod.cpp:566,588-591) after 300 steps of the default school, GPU ensemble against the reference's own sequential
+    update replayed by the oracle (48 replicates)"""
+    from fish_abm_b200 import synth
+    from fish_abm_b200.stats import speed_factor_hist
+    from oracle.pyoracle import Oracle, State
+    steps, RO = 300, 48
+    with Ensemble(R, n=60, seed=909, speed_norm=60.0) as E:
+        E.initialize(5.0)
+        E.set_quality(q100)
+        init = E.get_state()
+        E.step(steps)
+        g = E.get_state()
+    hg = speed_factor_hist(g["speed_factor"], 60.0)
+    sf_o = []
+    for r in range(RO):   # the same initial schools as the first RO replicates, sequential (reference-order) update
+        st = State(**{k: np.array(v[r]) for k, v in init.items()})
+        O = Oracle(st, 2000, 2000, q100.copy(), seed=909, replicate=r, speed_norm=60.0)
+        O.run(steps, sync=False, log_sumq=False)
+        sf_o.append(O.state.speed_factor.copy())
+    ho = speed_factor_hist(np.concatenate(sf_o), 60.0)
+    kmax = max(len(hg["front_count_hist"]), len(ho["front_count_hist"]))
+    pg = np.r_[hg["fed"], np.pad(hg["front_count_hist"], (0, kmax - len(hg["front_count_hist"])))] / hg["fish"]
+    po = np.r_[ho["fed"], np.pad(ho["front_count_hist"], (0, kmax - len(ho["front_count_hist"])))] / ho["fish"]
+    assert abs(hg["mean"] - ho["mean"]) < 0.08 * ho["mean"]
+    assert 0.5 * np.abs(pg - po).sum() < 0.15     # total-variation distance between the two histograms
+    assert abs(pg[0] - po[0]) < 0.05              # the share of fish that have just fed
