@@ -99,6 +99,9 @@ struct fishabm_ctx {
 
     Buffers buf[2];
     int cur = 0;
+    float4* rec_tmp = nullptr;   // moved records of a fused neighbour + update pass (kernels read buf[cur].rec meanwhile)
+    float4* rec_src = nullptr;   // where the coming sort finds the unsorted records: rec_tmp after a fused pass, else buf[cur].rec
+    bool fuse_update = true;     // FISHABM_FUSED_UPDATE=0 keeps K5 a separate launch
     int *next_cell = nullptr, *next_rank = nullptr, *cell_count = nullptr, *cell_start = nullptr, *tile_sums = nullptr;
     int4* cnt = nullptr;
     float* turn = nullptr;
@@ -223,7 +226,8 @@ cudaError_t preload_kernels() {
     L((const void*)in_zone_generic_kernel); L((const void*)index_by_id_kernel); L((const void*)ingest_incoming_kernel);
     L((const void*)ingest_kernel); L((const void*)neighbour_kernel<false>); L((const void*)neighbour_kernel<true>);
     L((const void*)neighbour_kernel_v2<false>); L((const void*)neighbour_kernel_v2<true>); L((const void*)scan_finish_kernel);
-    L((const void*)neighbour_kernel_v3<false>); L((const void*)neighbour_kernel_v3<true>);
+    L((const void*)neighbour_kernel_v3<false, false>); L((const void*)neighbour_kernel_v3<true, false>);
+    L((const void*)neighbour_kernel_v3<false, true>); L((const void*)neighbour_kernel_v3<true, true>);
     L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
     L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
     L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel); L((const void*)brute_fp64_pass_kernel);
@@ -251,10 +255,11 @@ int rebuild(fishabm_ctx* ctx) {
     }
     const Buffers& in = ctx->buf[ctx->cur];
     const Buffers& out = ctx->buf[ctx->cur ^ 1];
-    ScatterArgs s{in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap};
+    ScatterArgs s{ctx->rec_src ? ctx->rec_src : in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap};
     scatter_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(s);
     ctx->launches += 4;
     ctx->cur ^= 1;
+    ctx->rec_src = nullptr;
     CK(cudaGetLastError());
     return 0;
 }
@@ -262,7 +267,21 @@ int rebuild(fishabm_ctx* ctx) {
 enum { PASS_COUNTS = 1, PASS_TURN = 2 };
 
 // K4: one neighbour pass.  active_lag_max < 0 evaluates every fish (frozen-state queries).
-int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_t step_sample, uint32_t step_move, bool timed) {
+int split_for(const fishabm_ctx* ctx) {
+    // fewer cells than resident warps (small or dense schools): split every cell's fish over several work items
+    const int own_cells = ctx->g.own_c1 - ctx->g.own_c0;
+    int split = std::max(1, std::min(32, (2 * ctx->nb_grid * V2_WARPS) / std::max(1, own_cells)));
+    if (const char* sp = getenv("FISHABM_SPLIT")) split = std::max(1, std::min(32, atoi(sp)));
+    return split;
+}
+// the per-fish update can ride inside the neighbour kernel when a warp owns whole cells
+bool can_fuse_update(const fishabm_ctx* ctx) {
+    return ctx->fuse_update && ctx->nb_variant == 3 && ctx->p.mode == FISHABM_MODE_CELL_FP32 && !ctx->ens && split_for(ctx) == 1;
+}
+
+// fuse: the update (K5) to run inside the pass (see neighbour_kernel_v3<., true>), or null
+int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_t step_sample, uint32_t step_move, bool timed,
+                   const UpdateArgs* fuse = nullptr) {
     NvtxRange nv("fishabm: K4 neighbour pass");
     const Buffers& b = ctx->buf[ctx->cur];
     NeighArgs a;
@@ -293,7 +312,8 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     if (ctx->p.mode == FISHABM_MODE_BRUTE_FP64) {
         BrutePassArgs ba;
         ba.c = CheckArgs{b.rec, b.cold0, b.cold1, b.cell, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                         ctx->n, ctx->g, ctx->p.w, ctx->p.h, step_move, ctx->p.seed, ctx->p.replicate0, ctx->model};
+                         ctx->n, ctx->g, ctx->p.w, ctx->p.h, step_move, ctx->p.seed, ctx->p.replicate0, ctx->model,
+                         ctx->p.model.weight_align, ctx->p.model.weight_attract};
         ba.cnt = ctx->cnt; ba.turn = ctx->turn; ba.aux = ctx->aux;
         ba.active_lag_max = active_lag_max; ba.do_sample = do_sample ? 1 : 0; ba.step_sample = step_sample;
         brute_fp64_pass_kernel<<<cdiv(ctx->n * 32, 256), 256, 0, ctx->stream>>>(ba);
@@ -303,16 +323,19 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         else neighbour_kernel<false><<<grid, NB_THREADS, 0, ctx->stream>>>(a);
     } else {
         ctx->wc_parity ^= 1;
-        // fewer cells than resident warps (small or dense schools): split every cell's fish over several work items
-        a.split = std::max(1, std::min(32, (2 * ctx->nb_grid * V2_WARPS) / std::max(1, own_cells)));
-        if (const char* sp = getenv("FISHABM_SPLIT")) a.split = std::max(1, std::min(32, atoi(sp)));
+        a.split = split_for(ctx);
         const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V2_WARPS));
         if (ctx->nb_variant == 2) {
             if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
             else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+        } else if (fuse) {
+            if (ctx->stats_on) neighbour_kernel_v3<true, true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, *fuse);
+            else neighbour_kernel_v3<false, true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, *fuse);
         } else {
-            if (ctx->stats_on) neighbour_kernel_v3<true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a);
-            else neighbour_kernel_v3<false><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a);
+            UpdateArgs none;
+            memset(&none, 0, sizeof none);
+            if (ctx->stats_on) neighbour_kernel_v3<true, false><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, none);
+            else neighbour_kernel_v3<false, false><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, none);
         }
     }
     ctx->launches += 1;
@@ -353,11 +376,10 @@ int publish(fishabm_ctx* ctx) {
 }
 
 // K5 (+ deferred food-grid writes); a move also packs the slab messages
-int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
-    NvtxRange nv("fishabm: K5 update (sample / feed / move, slab message packing)");
+int make_update_args(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move, UpdateArgs* out) {
     const Buffers& b = ctx->buf[ctx->cur];
-    UpdateArgs u;
-    u.rec = b.rec; u.cold0 = b.cold0; u.cold1 = b.cold1; u.cell = b.cell; u.cell_start = ctx->cell_start;
+    UpdateArgs& u = *out;
+    u.rec = b.rec; u.rec_out = b.rec; u.cold0 = b.cold0; u.cold1 = b.cold1; u.cell = b.cell; u.cell_start = ctx->cell_start;
     u.cnt = ctx->cnt; u.turn = ctx->turn; u.aux = ctx->aux;
     u.next_cell = ctx->next_cell; u.next_rank = ctx->next_rank; u.next_count = ctx->cell_count;
     const int up = ctx->upd_parity;
@@ -371,6 +393,25 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     u.out_left = msg(ctx, ctx->out_left); u.out_right = msg(ctx, ctx->out_right);
     if (ctx->slab && do_move) { int rc = open_out_messages(ctx, &u.out_left, &u.out_right); if (rc) return rc; }
     u.part = UPD_ALL;
+    return 0;
+}
+
+// the deferred food-grid writes of a sample()
+int after_update(fishabm_ctx* ctx, bool do_sample) {
+    if (do_sample) {
+        const int up = ctx->upd_parity;
+        apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + up, ctx->upd_count + (up ^ 1), ctx->upd_idx, ctx->upd_val);
+        ctx->upd_parity ^= 1;
+        ctx->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_move) {
+    NvtxRange nv("fishabm: K5 update (sample / feed / move, slab message packing)");
+    UpdateArgs u;
+    { int rc = make_update_args(ctx, do_sample, do_move, step_move, &u); if (rc) return rc; }
     static const bool edges_first = !(getenv("FISHABM_EDGES_FIRST") && atoi(getenv("FISHABM_EDGES_FIRST")) == 0);
     if (ctx->slab && do_move && ctx->p2p && ctx->p.nranks > 1 && edges_first) {
         // edges first: the two outermost owned columns per side hold every migrant and ghost; their messages are
@@ -384,13 +425,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
-    if (do_sample) {
-        apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + up, ctx->upd_count + (up ^ 1), ctx->upd_idx, ctx->upd_val);
-        ctx->upd_parity ^= 1;
-        ctx->launches += 1;
-    }
-    CK(cudaGetLastError());
-    return 0;
+    return after_update(ctx, do_sample);
 }
 
 // after a move: (slab) take in the two received messages, then re-sort
@@ -398,7 +433,7 @@ int finish_move(fishabm_ctx* ctx, unsigned char* in_left, unsigned char* in_righ
     if (ctx->slab) {
         NvtxRange nv("fishabm: K1 ingest of received slab messages");
         const Buffers& b = ctx->buf[ctx->cur];
-        IncomingArgs a{msg(ctx, in_left), msg(ctx, in_right), b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count,
+        IncomingArgs a{msg(ctx, in_left), msg(ctx, in_right), ctx->rec_src ? ctx->rec_src : b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count,
                        ctx->cell_start, ctx->n_unsorted, ctx->err, ctx->cap, ctx->g};
         ingest_incoming_kernel<<<std::max(1, std::min(1024, cdiv(2 * (ctx->cap_m + ctx->cap_g), 256))), 256, 0, ctx->stream>>>(a);
         ctx->launches += 1;
@@ -713,6 +748,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(dalloc(&c->buf[k].rec, cap)); A(dalloc(&c->buf[k].cold0, cap)); A(dalloc(&c->buf[k].cold1, cap)); A(dalloc(&c->buf[k].cell, cap));
     }
     A(dalloc(&c->next_cell, cap)); A(dalloc(&c->next_rank, cap));
+    if (!ens) A(dalloc(&c->rec_tmp, cap));
+    if (const char* fu = getenv("FISHABM_FUSED_UPDATE")) c->fuse_update = atoi(fu) != 0;
     A(dalloc(&c->cell_count, (size_t)c->ncell + 1)); A(dalloc(&c->cell_start, (size_t)c->ncell + 1));
     A(dalloc(&c->tile_sums, (size_t)cdiv(c->ncell, SCAN_TILE) + 1));
     A(dalloc(&c->cnt, cap)); A(dalloc(&c->turn, cap)); A(dalloc(&c->aux, cap));
@@ -755,8 +792,10 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     if (ok) {
         A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
-        A(cudaFuncSetAttribute(neighbour_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
-        A(cudaFuncSetAttribute(neighbour_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");
     if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
@@ -766,7 +805,7 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
         static_assert(V2_WARPS == V3_WARPS && V2_THREADS == V3_THREADS, "the work split assumes the same CTA shape");
         if (c->nb_variant == 2) A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
-        else A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v3<false>, V3_THREADS, V3_SMEM_BYTES));
+        else A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v3<false, true>, V3_THREADS, V3_SMEM_BYTES));
         c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
         int scan_per_sm = 0;
         A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_per_sm, scan_fused_kernel, SCAN_THREADS, 0));
@@ -791,6 +830,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     for (void* q : c->ipc_opened) if (q) cudaIpcCloseMemHandle(q);
     cudaFree(c->inbox); cudaFree(c->ctr);
     for (int k = 0; k < 2; ++k) { cudaFree(c->buf[k].rec); cudaFree(c->buf[k].cold0); cudaFree(c->buf[k].cold1); cudaFree(c->buf[k].cell); }
+    cudaFree(c->rec_tmp);
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
@@ -1238,7 +1278,8 @@ int fishabm_check_fp64(fishabm_ctx* ctx, const int32_t* ids, int32_t k, int32_t*
     CK(cudaMemsetAsync(ctx->pos_of_id, 0xFF, (size_t)ctx->n * sizeof(int), s));
     index_by_id_kernel<<<cdiv(ctx->cap, 256), 256, 0, s>>>(b.cold1, ctx->cell_start, ctx->g, ctx->pos_of_id);
     CheckArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->pos_of_id, ctx->st_ids, k, ctx->st_i4, ctx->st_dir, ctx->st_lag,
-                ctx->n, ctx->g, ctx->p.w, ctx->p.h, ctx->step, ctx->p.seed, ctx->p.replicate0, ctx->model};
+                ctx->n, ctx->g, ctx->p.w, ctx->p.h, ctx->step, ctx->p.seed, ctx->p.replicate0, ctx->model,
+                ctx->p.model.weight_align, ctx->p.model.weight_attract};
     check_fp64_kernel<<<cdiv(k * 32, 256), 256, 0, s>>>(a);
     ctx->launches += 2;
     CK(cudaGetLastError());
@@ -1282,14 +1323,19 @@ int fishabm_sample(fishabm_ctx* ctx) {
 static int step_first_half(fishabm_ctx* ctx) {
     int rc;
     const uint32_t s = ctx->step;
-    if (ctx->pending_sample) {  // sample(s-1) and move(s) share one neighbour pass
-        if ((rc = neighbour_pass(ctx, 1, true, s - 1, s, true))) return rc;
+    const bool pend = ctx->pending_sample;  // sample(s-1) and move(s) share one neighbour pass
+    if (can_fuse_update(ctx)) {              // ... and the per-fish update rides inside it
+        UpdateArgs u;
+        if ((rc = make_update_args(ctx, pend, true, s, &u))) return rc;
+        u.rec_out = ctx->rec_tmp;
+        if ((rc = neighbour_pass(ctx, pend ? 1 : 0, pend, pend ? s - 1 : s, s, true, &u))) return rc;
+        ctx->rec_src = ctx->rec_tmp;
         if ((rc = phase_mark(ctx, 1))) return rc;
-        return update_launch(ctx, true, true, s);
+        return after_update(ctx, pend);
     }
-    if ((rc = neighbour_pass(ctx, 0, false, s, s, true))) return rc;
+    if ((rc = neighbour_pass(ctx, pend ? 1 : 0, pend, pend ? s - 1 : s, s, true))) return rc;
     if ((rc = phase_mark(ctx, 1))) return rc;
-    return update_launch(ctx, false, true, s);
+    return update_launch(ctx, pend, true, s);
 }
 
 static int step_untimed(fishabm_ctx* ctx, int nsteps) {

@@ -714,6 +714,8 @@ __device__ __forceinline__ void slab_push_ghost(const SlabMsg& m, const float4& 
 // K5: per-fish state transition
 // ------------------------------------------------------------------------------------------------------
 struct UpdateArgs {
+    float4* rec_out;    // where the moved record goes: `rec` itself (update_kernel: in place), or a scratch array when the
+                        // update runs inside the neighbour kernel, whose other warps still read `rec` as candidates
     float4* rec;
     float4* cold0;
     int4* cold1;
@@ -783,10 +785,9 @@ __global__ void slab_wait_kernel(const int* flag_left, const int* flag_right, in
 }
 
 // the state transition of the owned fish at sorted index i
-__device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
+__device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, const int mycell) {
     float4 c0 = a.cold0[i];
     int4 c1 = a.cold1[i];
-    const int mycell = a.cell[i];
     const uint32_t aux = a.do_sample ? a.aux[i] : 0u;
     const int ny = a.g.ny;
 
@@ -839,7 +840,7 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i) {
         }
         cy %= ny; if (cy < 0) cy += ny;
         const int newcell = cx * ny + cy;
-        a.rec[i] = r;
+        a.rec_out[i] = r;
         a.next_cell[i] = newcell;
         a.next_rank[i] = atomicAdd(&a.next_count[newcell], 1);
         if (a.slab) {
@@ -862,7 +863,7 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
     if (a.part == UPD_ALL) {  // one thread per held entry
         if (tid >= total) return;
         if (tid < b1 || tid >= e2) { if (a.do_move) a.next_cell[tid] = -1; return; }  // ghost: rebuilt by every exchange
-        update_fish(a, tid);
+        update_fish(a, tid, a.cell[tid]);
         return;
     }
     // owned fish = [b1,e1) (first two columns) + [e1,b2) (middle) + [b2,e2) (last two columns), contiguous in sorted order
@@ -874,12 +875,12 @@ __global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
         for (int t = tid; t < nl + nr + n1 + n2; t += nthreads) {
             if (t < nl) { if (a.do_move) a.next_cell[t] = -1; }
             else if (t < nl + nr) { if (a.do_move) a.next_cell[e2 + (t - nl)] = -1; }
-            else if (t < nl + nr + n1) update_fish(a, b1 + (t - nl - nr));
-            else update_fish(a, b2 + (t - nl - nr - n1));
+            else if (t < nl + nr + n1) { const int i = b1 + (t - nl - nr); update_fish(a, i, a.cell[i]); }
+            else { const int i = b2 + (t - nl - nr - n1); update_fish(a, i, a.cell[i]); }
         }
     } else {                    // UPD_MIDDLE: one thread per fish of the interior columns
         const int i = e1 + tid;
-        if (i < b2) update_fish(a, i);
+        if (i < b2) update_fish(a, i, a.cell[i]);
     }
 }
 
@@ -1249,6 +1250,7 @@ struct CheckArgs {
     int n; Grid g; int w, h;
     uint32_t step; uint64_t seed; uint32_t replicate;
     Model model;
+    double w_align, w_attract;   // the combination weights in double precision (Model keeps fp32 copies for the fp32 path)
 };
 enum { CHECK_RANDOMWALK = 1, CHECK_TIES = 2, CHECK_KNIFE = 4 };
 
@@ -1347,8 +1349,8 @@ __device__ __forceinline__ CheckOut check_eval(const CheckArgs& a, int fi, int i
     if (n_av > 0) turn = check_averageturn(avx, avy, n_av);             // :356-358
     else if (n_al > 0 && n_at > 0) {                                    // :360-365: weights 1.7 / 0.7
         const double A = check_averageturn(alx, aly, n_al), T = check_averageturn(atx, aty, n_at);
-        const double xs = cos(A * M_PI / 180.0) * (double)a.model.w_align + cos(T * M_PI / 180.0) * (double)a.model.w_attract;
-        const double ys = sin(A * M_PI / 180.0) * (double)a.model.w_align + sin(T * M_PI / 180.0) * (double)a.model.w_attract;
+        const double xs = cos(A * M_PI / 180.0) * a.w_align + cos(T * M_PI / 180.0) * a.w_attract;
+        const double ys = sin(A * M_PI / 180.0) * a.w_align + sin(T * M_PI / 180.0) * a.w_attract;
         turn = check_averageturn(xs, ys, 2);
     } else if (n_al > 0) turn = check_averageturn(alx, aly, n_al);
     else if (n_at > 0) turn = check_averageturn(atx, aty, n_at);

@@ -70,8 +70,12 @@ __device__ __forceinline__ void v3_setp_lt2(uint32_t a, uint32_t b, bool& plo, b
     plo = lo != 0; phi = hi != 0;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_kernel_v3(const NeighArgs a) {
+// FUSE: the warp that has finished the neighbour pass of a cell also runs the per-fish update (K5: sample / feed / move) of
+// that cell's fish right away -- their pass outputs are still in L1 / L2, the separate update kernel and its re-read of the
+// whole state disappear.  The moved records go to a scratch array (u.rec_out): `rec` must stay as it is while other warps
+// read it as candidates.  Everything else the update touches belongs to the cell's own fish or its own 10 x 10 food cells.
+template <bool STATS, bool FUSE>
+__global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_kernel_v3(const NeighArgs a, const UpdateArgs u) {
     extern __shared__ __align__(16) unsigned char v3_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -80,6 +84,11 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
 
     unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.work_counter_next = 0;
+    if (FUSE && u.slab && u.do_move) {   // last step's ghosts are dropped by the coming sort (update_kernel does this when unfused)
+        const int total = a.cell_start[a.g.ncell], b1 = a.cell_start[a.g.own_c0], e2 = a.cell_start[a.g.own_c1];
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < b1 + (total - e2); t += gridDim.x * blockDim.x)
+            u.next_cell[t < b1 ? t : e2 + (t - b1)] = -1;
+    }
     const int n_items = (a.g.own_c1 - a.g.own_c0) * a.split;
     const __half2 r2h = __float2half2_rn(V3_R2H);
     const uint32_t r2h_bits = *reinterpret_cast<const uint32_t*>(&r2h);
@@ -307,6 +316,13 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                 }
             }
             __syncwarp();
+        }
+        if (FUSE) {   // K5 for this cell's fish (the host only fuses with split == 1: the whole cell is this warp's)
+            __syncwarp();
+            for (int base = s0; base < e0; base += 32) {
+                const int i = base + lane;
+                if (i < e0) update_fish(u, i, c);
+            }
         }
     }
     if (STATS && a.stats && lane == 0) {
