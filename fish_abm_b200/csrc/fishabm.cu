@@ -101,7 +101,8 @@ struct fishabm_ctx {
     int cur = 0;
     float4* rec_tmp = nullptr;   // moved records of a fused neighbour + update pass (kernels read buf[cur].rec meanwhile)
     float4* rec_src = nullptr;   // where the coming sort finds the unsorted records: rec_tmp after a fused pass, else buf[cur].rec
-    bool fuse_update = true;     // FISHABM_FUSED_UPDATE=0 keeps K5 a separate launch
+    bool fuse_update = false;    // FISHABM_FUSED_UPDATE=1: K5 inside the neighbour kernel (measured SLOWER: 363 vs 249 + 45 us at C3,
+                                 // DESIGN.md section 3; kept as a bit-identical cross-check of the update's data flow)
     int *next_cell = nullptr, *next_rank = nullptr, *cell_count = nullptr, *cell_start = nullptr, *tile_sums = nullptr;
     int4* cnt = nullptr;
     float* turn = nullptr;
@@ -234,6 +235,15 @@ cudaError_t preload_kernels() {
     return e;
 }
 
+// a non-zero identifier of the physical GPU behind a device ordinal (the ordinal itself depends on CUDA_VISIBLE_DEVICES)
+int32_t gpu_identity(int device) {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return 1 + device; }
+    uint32_t h = 2166136261u;
+    for (const char* p = bus; *p; ++p) h = (h ^ (uint32_t)(unsigned char)*p) * 16777619u;
+    return (int32_t)(h | 1u);
+}
+
 SlabMsg msg(const fishabm_ctx* c, unsigned char* base, SlabHeader* counters = nullptr) { return SlabMsg{base, c->cap_m, c->cap_g, counters}; }
 // inbox layout: side 0 = messages from my left neighbour, side 1 = from my right; two slots per side (alternating
 // exchanges: a neighbour may already be packing exchange s+1 while exchange s is still being ingested here)
@@ -244,11 +254,22 @@ size_t inbox_flag_off(const fishabm_ctx* c, int side, int slot) { return 4 * c->
 int rebuild(fishabm_ctx* ctx) {
     NvtxRange nv("fishabm: K2 scan + K3 scatter (counting sort)");
     const int ntiles = cdiv(ctx->ncell, SCAN_TILE);
-    if (ntiles <= ctx->scan_resident) {  // every tile's block is resident at once: one launch
-        ScanFusedArgs f{ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start, ctx->scan_sync, ctx->scan_sync + 1, ++ctx->scan_epoch, ntiles};
-        scan_fused_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(f);
-        ctx->launches -= 2;
-    } else {
+    bool fused_scan = false;
+    if (ntiles <= ctx->scan_resident) {
+        // one launch: its blocks wait for the block that scans the tile sums, so they must all be resident at the same time.
+        // A COOPERATIVE launch makes the driver guarantee that (whatever else shares the GPU) or refuse the launch.
+        ScanFusedArgs f{ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start, ctx->scan_sync, ctx->scan_sync + 1, ctx->scan_epoch + 1, ntiles};
+        void* params[] = {&f};
+        if (cudaLaunchCooperativeKernel((const void*)scan_fused_kernel, dim3(ntiles), dim3(SCAN_THREADS), params, 0, ctx->stream) == cudaSuccess) {
+            ctx->scan_epoch += 1;
+            fused_scan = true;
+            ctx->launches -= 2;
+        } else {
+            cudaGetLastError();          // refused (not enough free SMs for a co-resident grid): the three-launch scan below
+            ctx->scan_resident = 0;
+        }
+    }
+    if (!fused_scan) {
         scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums);
         scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, ntiles);
         scan_finish_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start);
@@ -1528,6 +1549,7 @@ int fishabm_slab_get_endpoint(fishabm_ctx* ctx, fishabm_slab_endpoint* out) {
     out->raw_pointer = (uint64_t)(uintptr_t)ctx->inbox;
     out->bytes = (int64_t)ctx->inbox_bytes;
     out->pid = (int32_t)getpid(); out->device = ctx->p.device; out->rank = ctx->p.rank;
+    out->pad = gpu_identity(ctx->p.device);   // which physical GPU (hash of its PCI bus id): see fishabm_slab_attach
     return 0;
 }
 
@@ -1538,6 +1560,13 @@ int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, con
     if (left->rank != ctx->left || right->rank != ctx->right) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: endpoints of ranks %d / %d given, neighbours are %d / %d", left->rank, right->rank, ctx->left, ctx->right);
     if (left->bytes != (int64_t)ctx->inbox_bytes || right->bytes != (int64_t)ctx->inbox_bytes) return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: the neighbours' message capacities differ from mine");
     CK(cudaSetDevice(ctx->p.device));
+    // Kernels of ONE GPU cannot be relied on to run at the same time (one slab's wait kernel could keep the neighbour's
+    // kernels from ever being scheduled), so the peer-memory transport needs every slab on its own GPU.  Slabs that share a
+    // GPU exchange through the caller-driven hooks (fishabm_slab_begin_step / buffers / end_step).
+    const int32_t my_gpu = gpu_identity(ctx->p.device);
+    if (ctx->p.nranks > 1 && (left->pad == my_gpu || right->pad == my_gpu) && !getenv("FISHABM_ALLOW_SHARED_GPU_P2P"))
+        return fail(ctx, FISHABM_E_ARG, "fishabm_slab_attach: a neighbour slab lives on the same GPU; the peer-memory transport needs one GPU per slab "
+                                       "(use the caller-driven exchange: fishabm_slab_begin_step / fishabm_slab_buffers / fishabm_slab_end_step)");
     const fishabm_slab_endpoint* eps[2] = {left, right};
     unsigned char* ptr[2] = {nullptr, nullptr};
     for (int k = 0; k < 2; ++k) {

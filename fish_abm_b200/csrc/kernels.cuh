@@ -487,33 +487,31 @@ __device__ __forceinline__ void move_core(float4& r, float4& c0, int lag, int& c
                                           float speed_norm_inv2) {
     // fp32 throughout: the state is fp32 (heading ulp 3e-5 deg = 5e-7 rad, in-cell offset ulp 1.5e-5), so each result is
     // within one ulp of the fp64 evaluation -- far inside the 1e-5 rad / 1e-4 unit parity bars -- at a fraction of
-    // the instructions of the fp64 sincospi / floor
-    float dir = c0.x;
-    if (lag == 0) {
-        float d0 = dir;
-        if (d0 < 0.f) d0 += 360.f; else if (d0 >= 360.f) d0 -= 360.f;  // correctangle, :410-418
-        dir = d0 + (turn + (float)err);                                 // turn = social + error (:167), dir += turn (:169)
-        float sn, cs;
-        sincospif(dir / 180.f, &sn, &cs);
-        const float stepl = c0.y * c0.z;  // speed * OLD speed_factor (:171-172)
-        const float px = fmaf(stepl, cs, r.x), py = fmaf(stepl, sn, r.y);
-        if (rolling) c0.z = fmaf((float)front, speed_norm_inv2, 1.0f);  // get_speed: 1 + 2*count/num, :588-591
-        // periodic wrap (correct_coords, :466-480) in cell/offset form
-        // (multiplying by 1/200 may misplace a value within an ulp of a cell edge by one cell: the two fix-ups below
-        // bring the offset back into [0, 200) either way)
-        const float kx = floorf(px * (1.f / CELL_F)), ky = floorf(py * (1.f / CELL_F));
-        float ox = fmaf(-kx, CELL_F, px), oy = fmaf(-ky, CELL_F, py);
-        cx += (int)kx; cy += (int)ky;
-        if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
-        if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
-        if (ox < 0.f) { ox += CELL_F; cx -= 1; }
-        if (oy < 0.f) { oy += CELL_F; cy -= 1; }
-        r.x = ox; r.y = oy;
-    } else {
-        dir = dir + (float)err;  // :177-179
-    }
+    // the instructions of the fp64 sincospi / floor.
+    // Branch-free: a lagged fish (:177-179) is a moving fish with turn 0 (its heading is not re-wrapped) and step length 0, so
+    // that the lanes of a warp -- 40 % moving, 60 % lagged -- run ONE instruction stream (the separate branches left half
+    // the lanes idle: 15 threads per instruction in ncu).
+    const bool moving = lag == 0;
+    float d0 = c0.x;
+    if (moving) { if (d0 < 0.f) d0 += 360.f; else if (d0 >= 360.f) d0 -= 360.f; }   // correctangle, :410-418 (moving fish only, :166)
+    const float dir = moving ? d0 + (turn + (float)err) : c0.x + (float)err;       // :167-169 / :178
+    float sn, cs;
+    heading_vector(dir, cs, sn);   // the new heading is also the direction of the step
+    const float stepl = moving ? c0.y * c0.z : 0.f;  // speed * OLD speed_factor (:171-172); a lagged fish stays where it is
+    const float px = fmaf(stepl, cs, r.x), py = fmaf(stepl, sn, r.y);
+    if (moving && rolling) c0.z = fmaf((float)front, speed_norm_inv2, 1.0f);  // get_speed: 1 + 2*count/num, :588-591
+    // periodic wrap (correct_coords, :466-480) in cell/offset form
+    // (multiplying by 1/200 may misplace a value within an ulp of a cell edge by one cell: the two fix-ups below
+    // bring the offset back into [0, 200) either way)
+    const float kx = floorf(px * (1.f / CELL_F)), ky = floorf(py * (1.f / CELL_F));
+    float ox = fmaf(-kx, CELL_F, px), oy = fmaf(-ky, CELL_F, py);
+    cx += (int)kx; cy += (int)ky;
+    if (ox >= CELL_F) { ox -= CELL_F; cx += 1; }
+    if (oy >= CELL_F) { oy -= CELL_F; cy += 1; }
+    if (ox < 0.f) { ox += CELL_F; cx -= 1; }
+    if (oy < 0.f) { oy += CELL_F; cy -= 1; }
+    r.x = ox; r.y = oy; r.z = cs; r.w = sn;
     c0.x = dir;
-    heading_vector(dir, r.z, r.w);
 }
 
 template <bool STATS>

@@ -70,12 +70,21 @@ __device__ __forceinline__ void v3_setp_lt2(uint32_t a, uint32_t b, bool& plo, b
     plo = lo != 0; phi = hi != 0;
 }
 
+// K5 for the fish [s0, e0) of cell c, one fish per lane.  Deliberately NOT inlined: its registers (Philox, sincospi, the
+// feeding-rank loop) must not weigh on the allocation of the pair loops of the kernel that calls it once per cell.
+__device__ __noinline__ void v3_update_cell(const UpdateArgs* u, int s0, int e0, int c, int lane) {
+    for (int base = s0; base < e0; base += 32) {
+        const int i = base + lane;
+        if (i < e0) update_fish(*u, i, c);
+    }
+}
+
 // FUSE: the warp that has finished the neighbour pass of a cell also runs the per-fish update (K5: sample / feed / move) of
 // that cell's fish right away -- their pass outputs are still in L1 / L2, the separate update kernel and its re-read of the
 // whole state disappear.  The moved records go to a scratch array (u.rec_out): `rec` must stay as it is while other warps
 // read it as candidates.  Everything else the update touches belongs to the cell's own fish or its own 10 x 10 food cells.
 template <bool STATS, bool FUSE>
-__global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_kernel_v3(const NeighArgs a, const UpdateArgs u) {
+__global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_kernel_v3(const NeighArgs a, const __grid_constant__ UpdateArgs u) {
     extern __shared__ __align__(16) unsigned char v3_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -319,10 +328,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
         }
         if (FUSE) {   // K5 for this cell's fish (the host only fuses with split == 1: the whole cell is this warp's)
             __syncwarp();
-            for (int base = s0; base < e0; base += 32) {
-                const int i = base + lane;
-                if (i < e0) update_fish(u, i, c);
-            }
+            v3_update_cell(&u, s0, e0, c, lane);
         }
     }
     if (STATS && a.stats && lane == 0) {

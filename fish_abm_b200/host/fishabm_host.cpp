@@ -25,7 +25,12 @@ Backend::Backend(int n, const Structure& s, uint64_t seed, int device, int repli
         }
         ctxs_.push_back(c);
     }
-    if (nslabs > 1) {  // every slab learns where its two neighbours' inboxes are
+    // peer-memory transport only when every slab has its own GPU (kernels of one GPU cannot wait for each other); slabs that
+    // share a GPU are driven through the caller-driven exchange (step())
+    attached_ = nslabs > 1;
+    for (int r = 0; r < nslabs; ++r)
+        for (int q = r + 1; q < nslabs; ++q) if (slab_devices[r] == slab_devices[q]) attached_ = false;
+    if (attached_) {  // every slab learns where its two neighbours' inboxes are
         std::vector<fishabm_slab_endpoint> ep(nslabs);
         for (int r = 0; r < nslabs; ++r) ck(fishabm_slab_get_endpoint(ctxs_[r], &ep[r]), ctxs_[r]);
         for (int r = 0; r < nslabs; ++r) ck(fishabm_slab_attach(ctxs_[r], &ep[(r + nslabs - 1) % nslabs], &ep[(r + 1) % nslabs]), ctxs_[r]);
@@ -40,6 +45,21 @@ void Backend::ck(int rc, fishabm_ctx* c) const {
 
 void Backend::step(int nsteps) {
     if (ctxs_.size() == 1) { ck(fishabm_step(ctxs_[0], nsteps)); return; }
+    if (!attached_) {  // caller-driven exchange: what leaves through a slab's left edge arrives at its left neighbour's right side
+        const int k = (int)ctxs_.size();
+        std::vector<void*> ol(k), orr(k), il(k), ir(k);
+        int64_t bytes = 0;
+        for (int z = 0; z < nsteps; ++z) {
+            for (fishabm_ctx* c : ctxs_) ck(fishabm_slab_begin_step(c), c);
+            for (int r = 0; r < k; ++r) ck(fishabm_slab_buffers(ctxs_[r], &ol[r], &orr[r], &il[r], &ir[r], &bytes), ctxs_[r]);
+            for (int r = 0; r < k; ++r) {
+                ck(fishabm_slab_copy(ir[(r + k - 1) % k], ol[r], bytes), ctxs_[r]);
+                ck(fishabm_slab_copy(il[(r + 1) % k], orr[r], bytes), ctxs_[r]);
+            }
+            for (fishabm_ctx* c : ctxs_) ck(fishabm_slab_end_step(c), c);
+        }
+        return;
+    }
     for (int done = 0; done < nsteps;) {  // chunks short enough for the launch queues: nobody can finish before all are enqueued
         const int k = std::min(16, nsteps - done);
         for (fishabm_ctx* c : ctxs_) ck(fishabm_step_enqueue(c, k), c);

@@ -69,6 +69,7 @@ class Backend {
 
   private:
     std::vector<fishabm_ctx*> ctxs_;
+    bool attached_ = false;   // slabs attached to each other's inboxes (one GPU per slab); else the exchange is driven from step()
     int n_, reps_;
     Structure s_;
 };

@@ -139,8 +139,12 @@ class LocalSlabs:
         """transport "hooks": this class copies the messages (caller-driven exchange); "p2p": the slabs are attached
         to each other's inboxes and exchange by themselves (peer-memory transport, here inside one process)"""
         self.k = nslabs
-        self.transport = transport
         devices = devices or [0] * nslabs
+        if transport == "p2p" and len(set(devices)) < nslabs:
+            # kernels of one GPU cannot wait for each other (include/fishabm.h: fishabm_slab_attach): slabs that share a
+            # GPU are driven through the hooks
+            transport = "hooks"
+        self.transport = transport
         self.S = [School(rank=r, nranks=nslabs, device=devices[r], force_slab=True, **kw) for r in range(nslabs)]
         self.n, self.w, self.h = self.S[0].n, self.S[0].w, self.S[0].h
         if transport == "p2p":

@@ -257,9 +257,13 @@ typedef struct fishabm_slab_endpoint {
     unsigned char ipc_handle[64];  /* cudaIpcMemHandle_t of the inbox allocation */
     uint64_t raw_pointer;          /* the same allocation's device pointer, valid inside the owning process */
     int64_t bytes;                 /* size of the inbox allocation */
-    int32_t pid, device, rank, pad;
+    int32_t pid, device, rank;
+    int32_t pad;                   /* identifier of the physical GPU (filled by fishabm_slab_get_endpoint) */
 } fishabm_slab_endpoint;
 int fishabm_slab_get_endpoint(fishabm_ctx* ctx, fishabm_slab_endpoint* out);
+/* Every slab must be on its OWN GPU: kernels of one GPU are not guaranteed to run concurrently, so a slab waiting (on the
+ * device) for a neighbour on the same GPU could wait forever.  fishabm_slab_attach refuses such an attachment with
+ * FISHABM_E_ARG; slabs that share a GPU use the caller-driven exchange above. */
 int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, const fishabm_slab_endpoint* right);
 /* Slab-local state (what a rank of a large run should use: no rank ever holds the whole school).
  * fishabm_set_state_owned: `count` fish with global ids ids[], every one inside this slab's columns (x in

@@ -52,7 +52,9 @@ def test_slabs_stay_identical_over_600_steps(q100, monkeypatch):
         S.set_state(**d); S.set_quality(q); S.step(steps)
         g, qa = S.get_state(), S.get_quality()
     check_invariants(g, w, w, qa, int(q.sum()))
-    with LocalSlabs(4, transport="p2p", n=n, w=w, h=w, seed=204) as P:
+    import torch
+    devices = list(range(4)) if torch.cuda.device_count() >= 4 else None   # one GPU per slab: peer memory; else the hooks
+    with LocalSlabs(4, devices=devices, transport="p2p", n=n, w=w, h=w, seed=204) as P:
         P.set_state(**d); P.set_quality(q)
         owned0 = [s.slab_info()["owned"] for s in P.S]
         P.step(steps)

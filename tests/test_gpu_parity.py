@@ -384,3 +384,22 @@ def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
     O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, q.copy(), seed=17)
     ids = np.r_[np.arange(0, 5000, 97), np.arange(5000, n, 1021)].astype(np.int32)
     assert np.array_equal(res[2][0][ids], O.zone_counts(ids))
+
+
+def test_update_fused_into_the_neighbour_kernel_is_bit_identical(q100, monkeypatch):
+    """FISHABM_FUSED_UPDATE=1 runs K5 (sample / feed / move) inside the neighbour kernel, cell by cell, instead of as its own
+    launch: every field and the food grid must come out identical (whole school and a lone slab with halo columns)"""
+    n, w = 40_000, 6_000
+    d = synth.uniform_state(n, w, w, seed=141)
+    q = synth.tile_quality(q100, w, w)
+    res = []
+    for fused, slab in (("0", False), ("1", False), ("1", True)):
+        monkeypatch.setenv("FISHABM_FUSED_UPDATE", fused)
+        with School(n=n, w=w, h=w, seed=23, force_slab=slab) as S:
+            S.set_state(**d); S.set_quality(q)
+            S.step(7)
+            res.append((S.get_state(), S.get_quality(), S.zone_counts()))
+    for other in (1, 2):
+        for k in res[0][0]:
+            assert np.array_equal(res[0][0][k], res[other][0][k]), (other, k)
+        assert np.array_equal(res[0][1], res[other][1]) and np.array_equal(res[0][2], res[other][2])

@@ -71,15 +71,26 @@ def test_local_slabs_equal_whole_school(q100, nslabs):
         assert P.sum_array() == int(qa.sum())
 
 
+def gpus_for(nslabs):
+    """one GPU per slab, or skip: the peer-memory transport waits on the device for the neighbour's kernels, and kernels of
+    ONE GPU are not guaranteed to run at the same time (B200_PROFILING.md; fishabm_slab_attach refuses shared GPUs)"""
+    import torch
+    if torch.cuda.device_count() < nslabs:
+        pytest.skip(f"peer-memory transport needs one GPU per slab ({nslabs})")
+    return list(range(nslabs))
+
+
 @pytest.mark.parametrize("nslabs", [2, 3, 5])
 def test_peer_memory_transport_in_one_process(q100, nslabs, monkeypatch):
-    """the slabs pack straight into each other's inboxes and synchronise with device-side flags (here all on one GPU)"""
+    """the slabs pack straight into each other's inboxes and synchronise with device-side flags (one process, one GPU per slab)"""
+    devices = gpus_for(nslabs)
     monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "4000")
     n, w, steps = 30_000, 7 * 200 * 2, 21
     d = synth.uniform_state(n, w, w, seed=43, speed=12.0)
     q = synth.tile_quality(q100, w, w)
     zc0, g, qa, zc1, turn = whole_school(n, w, d, q, 78, steps)
-    with LocalSlabs(nslabs, transport="p2p", n=n, w=w, h=w, seed=78) as P:
+    with LocalSlabs(nslabs, devices=devices, transport="p2p", n=n, w=w, h=w, seed=78) as P:
+        assert P.transport == "p2p"
         P.set_state(**d)
         P.set_quality(q)
         P.step(steps)
@@ -93,13 +104,14 @@ def test_slab_local_state_round_trip_and_halo_refresh(q100, monkeypatch):
     """set_state_owned / get_state_owned: every slab is given only its own fish, the halos come from one exchange; the
     run must continue exactly like the whole school"""
     from fish_abm_b200 import FishAbmError
+    devices = gpus_for(3)
     monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "4000")
     n, w = 30_000, 7 * 200 * 2
     d = synth.uniform_state(n, w, w, seed=49, speed=12.0)
     q = synth.tile_quality(q100, w, w)
     _, g10, _, _, _ = whole_school(n, w, d, q, 80, 10)
     _, g20, qa20, zc20, turn20 = whole_school(n, w, d, q, 80, 20)
-    with LocalSlabs(3, transport="p2p", n=n, w=w, h=w, seed=80) as P:
+    with LocalSlabs(3, devices=devices, transport="p2p", n=n, w=w, h=w, seed=80) as P:
         P.set_state(**d)
         P.set_quality(q)
         P.step(10)
@@ -137,10 +149,11 @@ def test_slab_local_state_round_trip_and_halo_refresh(q100, monkeypatch):
 def test_peer_memory_timeout_is_reported_not_hung(q100, monkeypatch):
     """a neighbour that never steps: the wait kernel gives up after the timeout and the call reports it"""
     from fish_abm_b200 import FishAbmError
+    devices = gpus_for(2)
     monkeypatch.setenv("FISHABM_SLAB_TIMEOUT_MS", "300")
     n, w = 5_000, 2000
     d = synth.uniform_state(n, w, w, seed=48)
-    with LocalSlabs(2, transport="p2p", n=n, w=w, h=w, seed=3) as P:
+    with LocalSlabs(2, devices=devices, transport="p2p", n=n, w=w, h=w, seed=3) as P:
         P.set_state(**d)
         P.set_quality(q100)
         P.S[0].step_enqueue(1)
@@ -241,3 +254,46 @@ def test_multi_gpu_slabs_equal_whole_school(q100, tmp_path, nranks, transport, m
         assert np.array_equal(res[k], g[k]), k
     assert np.array_equal(res["quality"], qa)
     assert np.array_equal(res["zone"], zc1)
+
+
+def test_lone_slab_local_state_round_trip(q100):
+    """set_state_owned / get_state_owned on ONE slab that is its own neighbour (force_slab): runs on a single GPU and keeps
+    the slab-local state path covered there; the run continues exactly like the whole school"""
+    n, w = 20_000, 2400
+    d = synth.uniform_state(n, w, w, seed=61, speed=12.0)
+    q = synth.tile_quality(q100, w, w)
+    _, g20, qa20, zc20, _ = whole_school(n, w, d, q, 82, 20)
+    with School(n=n, w=w, h=w, seed=82, force_slab=True) as S:
+        S.set_state(**d); S.set_quality(q)
+        S.step(10)
+        own = S.get_state_owned()
+        assert np.array_equal(np.sort(own["ids"]), np.arange(n))
+        perm = np.random.default_rng(1).permutation(n)
+        S.set_state_owned(**{k: v[perm] for k, v in own.items()})
+        S.step_index = 10
+        S.step(10)
+        assert_same(S.get_state(), g20)
+        assert np.array_equal(S.get_quality(), qa20)
+        assert np.array_equal(S.zone_counts(), zc20)
+        bad = {k: v[:4].copy() for k, v in own.items()}
+        bad["ids"][2] = n + 5        # ids index device and host arrays: anything outside [0, n) is refused up front
+        from fish_abm_b200 import FishAbmError
+        with pytest.raises(FishAbmError) as e:
+            S.set_state_owned(**bad)
+        assert e.value.code == -1 and "outside [0" in str(e.value)
+
+
+def test_peer_memory_attach_refuses_a_shared_gpu(q100):
+    """two slabs on ONE GPU cannot wait for each other on the device: fishabm_slab_attach says so (and LocalSlabs falls back
+    to the caller-driven exchange)"""
+    from fish_abm_b200 import FishAbmError
+    A = School(n=4000, w=2000, h=2000, rank=0, nranks=2, device=0)
+    B = School(n=4000, w=2000, h=2000, rank=1, nranks=2, device=0)
+    try:
+        with pytest.raises(FishAbmError) as e:
+            A.slab_attach(B.slab_endpoint(), B.slab_endpoint())
+        assert e.value.code == -1 and "same GPU" in str(e.value)
+    finally:
+        A.close(); B.close()
+    with LocalSlabs(2, transport="p2p", n=4000, w=2000, h=2000, seed=1) as P:
+        assert P.transport == "hooks"
