@@ -385,13 +385,26 @@ def ours(args, rank: int, world: int, local_rank: int):
     fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     per_launch_ms = nb_ms / max(nb_launches, 1)
     achieved = flops_alg(cand, inter) / (per_launch_ms * 1e-3) / 1e12
-    cap = ncu_capture("neighbour_kernel_v2")
-    roofline = {"bound": "fp32", "kernel": "neighbour_kernel_v2", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+    kname = {"v1": "neighbour_kernel<", "v2": "neighbour_kernel_v2"}.get(os.environ.get("FISHABM_NEIGHBOUR", ""), "neighbour_kernel_v3")
+    cap = ncu_capture(kname)
+    # issue-slot fraction: the kernel is bound by instruction issue, not by the FP32 pipe, so the fraction of the SMs' issue
+    # slots (SMs x 4 schedulers x clock x launch time) it fills says more than flops / peak.  ncu measures it directly for the
+    # captured launch (smsp__issue_active); for the timed launches it is estimated from the capture's warp instructions per
+    # focal fish x the live focal count.
+    issue = None
+    if cap and cap.get("warp_instructions") and cap.get("focal_per_launch"):
+        slots = sm_count * 4 * peaks.get("sm_max_mhz", 1965.0) * 1e6 * per_launch_ms * 1e-3
+        issue = {"ncu_issue_active_pct": cap.get("issue_active_pct"), "warp_instructions_per_focal_fish": cap["warp_instructions"] / cap["focal_per_launch"],
+                 "estimated_frac_timed_launches": cap["warp_instructions"] / cap["focal_per_launch"] * focal / slots,
+                 "how": "ncu: smsp__issue_active of the captured launch; estimate: (capture's warp instructions / its focal fish) x live focal fish / (SMs x 4 x sm_max_mhz x launch time)"}
+    roofline = {"bound": "fp32", "kernel": kname.rstrip("<"), "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak, "traffic": cap["dram_bytes"] if cap else None,
                 "traffic_note": "ncu dram__bytes_read+write of one launch (the 1M-fish state is L2-resident: 16 B x 1M hot records)" if cap else None,
-                "ncu": {k: cap[k] for k in ("issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct", "warp_instructions", "registers", "source") if k in cap} if cap else None,
-                "binding_limit": "instruction issue: the pair loop needs ~100 issued instructions per interacting pair (compares, selects, "
-                                 "ballots, polynomial atan2, MUFU) of which SURVEY 8(d)'s convention counts 20 flops; see DESIGN.md section 3",
+                "issue_slots": issue,
+                "ncu": {k: cap[k] for k in ("duration", "issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct", "warp_instructions", "threads_per_instruction", "registers", "source") if k in cap} if cap else None,
+                "binding_limit": "instruction issue (85 % of the issue slots are used): an interacting pair costs ~115 issued instructions per 32 pairs "
+                                 "(geometry, rounding bands, polynomial atan2, weight, MUFU sin/cos, fixed-point sums) of which SURVEY 8(d)'s convention counts "
+                                 "20 flops, and a candidate ~0.4 (packed-fp16 disc filter) of which it counts 13; see DESIGN.md section 3",
                 "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock); FP32 is not in MEASURED_PEAKS.json",
                 "flops_per_launch": flops_alg(cand, inter), "candidates_per_launch": cand, "interacting_per_launch": inter,
                 "focal_per_launch": focal, "launch_ms": per_launch_ms, "share_of_step": nb_ms / total_ms}

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                     const int k = 3 * ky + kx;
                     const int pk = S.run_pre[k];
                     u[kx] = max(pk, base) + lane; hi[kx] = min(S.run_pre[k + 1], base + fill); src[kx] = S.run_start[k] - pk;
+                    r[kx] = far;   // (initialised: an undefined value would be carried, through local memory, across the ky iterations)
                     if (u[kx] < hi[kx]) r[kx] = __ldg(&a.rec[src[kx] + u[kx]]);
                 }
                 const float sy = (float)(ky - 1) * CELL_F;

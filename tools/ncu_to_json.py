@@ -1,4 +1,7 @@
-"""Key metrics of every kernel in an .ncu-rep as JSON (one object per captured launch).  usage: ncu_to_json.py rep out.json"""
+"""Key metrics of every kernel in an .ncu-rep as JSON (one object per captured launch).
+usage: ncu_to_json.py rep out.json [ncu_target_stats.json launch_index]
+The optional pair (written by tools/ncu_target.py) adds the focal / candidate / interacting counts of the captured neighbour
+launch, from which bench.py derives warp instructions per focal fish."""
 import csv, json, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -23,5 +26,10 @@ for r in rows[2:]:
             d[k] = num(r[H.index(m)], U[H.index(m)])
     if "dram_read" in d: d["dram_bytes"] = d["dram_read"] + d["dram_write"]
     res.append(d)
+if len(sys.argv) > 4:
+    st = json.load(open(sys.argv[3]))["per_neighbour_launch"][int(sys.argv[4])]
+    for d in res:
+        if d["kernel"].startswith("neighbour_kernel"):
+            d.update(focal_per_launch=st["focal"], candidates_per_launch=st["candidates"], interacting_per_launch=st["interacting"])
 json.dump({"source": rep.split("/")[-1], "units": "duration us, bytes, percent", "launches": res}, open(out, "w"), indent=1)
 print(json.dumps(res)[:600])
