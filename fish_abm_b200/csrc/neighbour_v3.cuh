@@ -36,7 +36,7 @@ constexpr int V3_WARPS = 8;
 constexpr int V3_THREADS = V3_WARPS * 32;
 constexpr int V3_SLOTS = 256;         // window slots (queue entries are bytes); the last one is a permanent far-away candidate
 constexpr int V3_WIN = V3_SLOTS - 1;  // candidates per window batch: <= 255, so that the 8-bit packed counts cannot overflow
-constexpr int V3_FMAX = 12;           // focal fish per group
+constexpr int V3_FMAX = 16;           // focal fish per group
 constexpr float V3_FAR_X = 1.0e18f, V3_FAR_Y = 3.0e17f;   // padding candidate: beyond every radius, +inf in fp16; not on a lattice bearing
 constexpr float V3_HSCALE = 0.25f, V3_HCENTRE = 100.f;
 constexpr float V3_R2H = 2528.f;
