@@ -296,16 +296,16 @@ def small_configs_leg(device: int, with_cpu: bool):
     return out
 
 
-def ensemble_key(device: int, schools: int, steps: int = 20):
+def ensemble_key(device: int, schools: int, steps: int = 20, replicate0: int = 0):
     """BASELINE.json configs[4] on this rank's GPU: `schools` replicate schools of 200 fish sweeping speed (2.5..20),
     sample-rate reset (15/30/45) and fed speed factor (0.25/0.5/0.75) per school; K steps in ONE launch"""
     from fish_abm_b200 import Ensemble
     q100 = np.loadtxt(os.path.join(ROOT, "tests", "golden", "quality.csv"), delimiter=",", dtype=np.int32)
     n = 200
-    E = Ensemble(schools, n=n, seed=0x5EED, replicate0=0, device=device, speed_norm=float(n))
+    E = Ensemble(schools, n=n, seed=0x5EED, replicate0=replicate0, device=device, speed_norm=float(n))
     E.initialize(5.0)
     g = E.get_state()
-    g["speed"][:] = np.array([2.5, 5, 7.5, 10, 12.5, 15, 17.5, 20])[(np.arange(schools) % 8)][:, None]
+    g["speed"][:] = np.array([2.5, 5, 7.5, 10, 12.5, 15, 17.5, 20])[((np.arange(schools) + replicate0) % 8)][:, None]
     E.set_state(**g)
     E.set_quality(q100)
     swept = E.sweep_default() if hasattr(E, "sweep_default") else None

@@ -399,7 +399,8 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
             S2.close()
         except Exception as e:  # noqa: BLE001
             transports[other] = {"error": str(e)[:300]}
-    ens = ensemble_key(local_rank, max(1, args.schools // world)) if not getattr(args, "no_ensemble", False) else None
+    per_rank = max(1, args.schools // world)   # replicate ids rank * per_rank ...: part of the Philox key, no two ranks run the same school
+    ens = ensemble_key(local_rank, per_rank, replicate0=rank * per_rank) if not getattr(args, "no_ensemble", False) else None
     if ens is not None:   # replicates are independent: every rank ran schools/world of them, slowest rank sets the time
         ems, = allmax(ens["ms_per_step"])
         eat, = allsum(ens["food_eaten"])
