@@ -151,6 +151,16 @@ __device__ __forceinline__ void unit_vector_fp64(float dir_deg, double& c, doubl
     c = cos(ang); s = sin(ang);
 }
 
+// (column, row) of a column-major cell index without an integer division (~25 instructions each): the fp32 quotient is
+// within one or two of the true one for any grid, and the remainder fixes it up exactly
+__device__ __forceinline__ void cell_xy(int c, int ny, int& cx, int& cy) {
+    int q = (int)(__int2float_rz(c) * __frcp_rn(__int2float_rn(ny)));
+    int r = c - q * ny;
+    while (r < 0) { q -= 1; r += ny; }     // (at most one iteration up to ~4M columns; a loop so that it is exact beyond)
+    while (r >= ny) { q += 1; r -= ny; }
+    cx = q; cy = r;
+}
+
 // Literal fp64 restatement of the per-pair predicates of in_zone (fish_mod.cpp:237-254) for a pair whose fp32
 // evaluation fell inside a rounding band.  dx,dy are exact (offsets are fp32, cell shifts are multiples of 200).
 // Products and sums are kept unfused so the operation order is the reference's.
@@ -788,6 +798,8 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
     int4 c1 = a.cold1[i];
     const uint32_t aux = a.do_sample ? a.aux[i] : 0u;
     const int ny = a.g.ny;
+    int cx0, cy0;
+    cell_xy(mycell, ny, cx0, cy0);
 
     if (a.do_sample) {  // sample(), fish_mod.cpp:546-556
         if (aux & AUX_WANTS) {
@@ -796,17 +808,18 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
             // id order (the reference's loop order, :541): rank = feeders of this food cell with a lower id.
             const uint32_t key = aux & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS);
             const int s = a.cell_start[mycell], e = a.cell_start[mycell + 1];
-            int rank = 0, total = 0;
+            int rank = 0, total = 1;   // the fish itself; a second feeder on the same 20 x 20 food cell is rare (~3 %)
             for (int j = s; j < e; ++j) {
                 const uint32_t aj = a.aux[j];
-                if ((aj & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS)) == key) {
+                if (j != i && (aj & ((AUX_FOOD_MASK << AUX_FOOD_SHIFT) | AUX_WANTS)) == key) {
                     total++;
                     rank += (a.cold1[j].w < c1.w) ? 1 : 0;
                 }
             }
             const int fl = (int)((aux >> AUX_FOOD_SHIFT) & AUX_FOOD_MASK);
-            const int gx = (mycell / ny - a.g.own_c0 / ny) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
-            const int gy = (mycell % ny) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
+            const int fly = (fl * 205) >> 11, flx = fl - fly * FOOD_PER_CELL;   // fl / 10, fl % 10 for fl < 100
+            const int gx = (cx0 - (a.g.wrap_x ? 0 : 1)) * FOOD_PER_CELL + flx;   // owned columns start at local column 0 (whole school) or 1 (slab)
+            const int gy = cy0 * FOOD_PER_CELL + fly;
             const int qi = gy * a.qcols + gx;
             const int q = (int)a.quality[qi];
             if (rank < q) { c0.z = a.model.fed_sf; c1.z += 1; c1.y = a.model.rate_fed; }
@@ -823,20 +836,21 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
     if (a.do_move) {  // move(), fish_mod.cpp:165-179
         const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -a.model.error_range, a.model.error_range);
         float4 r = a.rec[i];
-        int cx = mycell / ny, cy = mycell % ny;
+        int cx = cx0, cy = cy0;
         const bool moving = c1.x == 0;
         move_core(r, c0, c1.x, cx, cy, moving ? a.turn[i] : 0.f, moving ? a.cnt[i].w : 0, err, a.rolling, a.speed_norm_inv2);
-        if (a.g.wrap_x) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
-        else {
+        if (a.g.wrap_x) {   // only a fish that crosses the world's edge pays for the modulo
+            if (cx < 0 || cx >= a.g.lnx) { cx %= a.g.lnx; if (cx < 0) cx += a.g.lnx; }
+        } else {
             // slabs: a fish may advance at most one column per step (the halo is one column wide, and with the edges-first
             // update a fish of an interior column must not reach a boundary or halo column after the messages have left)
-            const int cx_old = mycell / ny;
+            const int cx_old = cx0;
             if (cx < cx_old - 1 || cx > cx_old + 1 || cx < 0 || cx >= a.g.lnx) {
                 atomicOr(a.err, ERR_STEP_TOO_LONG);
                 cx = max(0, min(cx, a.g.lnx - 1));
             }
         }
-        cy %= ny; if (cy < 0) cy += ny;
+        if (cy < 0 || cy >= ny) { cy %= ny; if (cy < 0) cy += ny; }
         const int newcell = cx * ny + cy;
         a.rec_out[i] = r;
         a.next_cell[i] = newcell;
