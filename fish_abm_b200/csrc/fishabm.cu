@@ -100,6 +100,7 @@ struct fishabm_ctx {
     Buffers buf[2];
     int cur = 0;
     float4* rec_tmp = nullptr;   // moved records of a fused neighbour + update pass (kernels read buf[cur].rec meanwhile)
+    int apply_up = -1;           // >= 0: the deferred food-grid writes of upd_count[apply_up] ride in the coming scatter
     float4* rec_src = nullptr;   // where the coming sort finds the unsorted records: rec_tmp after a fused pass, else buf[cur].rec
     bool fuse_update = false;    // FISHABM_FUSED_UPDATE=1: K5 inside the neighbour kernel (measured SLOWER: 363 vs 249 + 45 us at C3,
                                  // DESIGN.md section 3; kept as a bit-identical cross-check of the update's data flow)
@@ -276,8 +277,20 @@ int rebuild(fishabm_ctx* ctx) {
     }
     const Buffers& in = ctx->buf[ctx->cur];
     const Buffers& out = ctx->buf[ctx->cur ^ 1];
-    ScatterArgs s{ctx->rec_src ? ctx->rec_src : in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap};
-    scatter_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(s);
+    ScatterArgs s{ctx->rec_src ? ctx->rec_src : in.rec, in.cold0, in.cold1, out.rec, out.cold0, out.cold1, out.cell, ctx->next_cell, ctx->next_rank, ctx->cell_start, ctx->n_unsorted, ctx->cap,
+                  nullptr, nullptr, nullptr, nullptr, nullptr};
+    const int sgrid = cdiv(ctx->cap, 256);
+    if (ctx->apply_up >= 0) {
+        if (sgrid >= SCATTER_APPLY_BLOCKS) {
+            s.quality = ctx->quality; s.upd_count = ctx->upd_count + ctx->apply_up; s.upd_count_next = ctx->upd_count + (ctx->apply_up ^ 1);
+            s.upd_idx = ctx->upd_idx; s.upd_val = ctx->upd_val;
+        } else {   // tiny school: the scatter has fewer blocks than the apply loop assumes
+            apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + ctx->apply_up, ctx->upd_count + (ctx->apply_up ^ 1), ctx->upd_idx, ctx->upd_val);
+            ctx->launches += 1;
+        }
+        ctx->apply_up = -1;
+    }
+    scatter_kernel<<<sgrid, 256, 0, ctx->stream>>>(s);
     ctx->launches += 4;
     ctx->cur ^= 1;
     ctx->rec_src = nullptr;
@@ -417,13 +430,16 @@ int make_update_args(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t st
     return 0;
 }
 
-// the deferred food-grid writes of a sample()
-int after_update(fishabm_ctx* ctx, bool do_sample) {
+// the deferred food-grid writes of a sample(): inside the coming sort's scatter when one follows (a move), else their own launch
+int after_update(fishabm_ctx* ctx, bool do_sample, bool sort_follows) {
     if (do_sample) {
         const int up = ctx->upd_parity;
-        apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + up, ctx->upd_count + (up ^ 1), ctx->upd_idx, ctx->upd_val);
+        if (sort_follows) ctx->apply_up = up;
+        else {
+            apply_quality_updates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->quality, ctx->upd_count + up, ctx->upd_count + (up ^ 1), ctx->upd_idx, ctx->upd_val);
+            ctx->launches += 1;
+        }
         ctx->upd_parity ^= 1;
-        ctx->launches += 1;
     }
     CK(cudaGetLastError());
     return 0;
@@ -446,7 +462,7 @@ int update_launch(fishabm_ctx* ctx, bool do_sample, bool do_move, uint32_t step_
     }
     update_kernel<<<cdiv(ctx->cap, 256), 256, 0, ctx->stream>>>(u);
     ctx->launches += 1;
-    return after_update(ctx, do_sample);
+    return after_update(ctx, do_sample, do_move);
 }
 
 // after a move: (slab) take in the two received messages, then re-sort
@@ -1352,7 +1368,7 @@ static int step_first_half(fishabm_ctx* ctx) {
         if ((rc = neighbour_pass(ctx, pend ? 1 : 0, pend, pend ? s - 1 : s, s, true, &u))) return rc;
         ctx->rec_src = ctx->rec_tmp;
         if ((rc = phase_mark(ctx, 1))) return rc;
-        return after_update(ctx, pend);
+        return after_update(ctx, pend, true);
     }
     if ((rc = neighbour_pass(ctx, pend ? 1 : 0, pend, pend ? s - 1 : s, s, true))) return rc;
     if ((rc = phase_mark(ctx, 1))) return rc;

@@ -854,7 +854,16 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
         const int newcell = cx * ny + cy;
         a.rec_out[i] = r;
         a.next_cell[i] = newcell;
-        a.next_rank[i] = atomicAdd(&a.next_count[newcell], 1);
+        {   // claim a rank in the new cell: one atomic per group of lanes that go to the SAME cell (neighbouring threads are
+            // neighbouring fish, so a warp targets two or three cells) instead of 32 same-address atomics the L2 serialises
+            const unsigned act = __activemask();
+            const unsigned peers = __match_any_sync(act, newcell);
+            const int leader = __ffs(peers) - 1, lane = (int)(threadIdx.x & 31u);
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&a.next_count[newcell], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            a.next_rank[i] = base + __popc(peers & ((1u << lane) - 1u));
+        }
         if (a.slab) {
             // crossing into a halo column = leaving the slab: the full state goes to that neighbour (the local
             // copy stays behind as next step's ghost); standing in a boundary column = being the neighbour's ghost
@@ -1145,8 +1154,16 @@ struct ScatterArgs {
     float4* rec_out; float4* cold0_out; int4* cold1_out; int* cell_out;
     const int* next_cell; const int* next_rank; const int* start;
     const int* n_unsorted; int cap;
+    // the deferred food-grid writes of the sample() that preceded this sort ride along (one launch less per step); null: none
+    uint8_t* quality; const int* upd_count; int* upd_count_next; const int* upd_idx; const uint8_t* upd_val;
 };
+constexpr int SCATTER_APPLY_BLOCKS = 64;
 __global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
+    if (a.quality && blockIdx.x < SCATTER_APPLY_BLOCKS) {   // = apply_quality_updates_kernel (nothing in this kernel reads the grid)
+        const int n = *a.upd_count;
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.upd_count_next = 0;
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += SCATTER_APPLY_BLOCKS * blockDim.x) a.quality[a.upd_idx[k]] = a.upd_val[k];
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(*a.n_unsorted, a.cap)) return;  // claims beyond the capacity were refused (and reported)
     const int c = a.next_cell[i];
