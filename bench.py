@@ -385,7 +385,7 @@ def ours(args, rank: int, world: int, local_rank: int):
     fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
     per_launch_ms = nb_ms / max(nb_launches, 1)
     achieved = flops_alg(cand, inter) / (per_launch_ms * 1e-3) / 1e12
-    kname = {"v1": "neighbour_kernel<", "v2": "neighbour_kernel_v2"}.get(os.environ.get("FISHABM_NEIGHBOUR", ""), "neighbour_kernel_v3")
+    kname = {"v1": "neighbour_kernel<", "v3": "neighbour_kernel_v3"}.get(os.environ.get("FISHABM_NEIGHBOUR", ""), "neighbour_kernel_v4")
     cap = ncu_capture(kname)
     # issue-slot fraction: the kernel is bound by instruction issue, not by the FP32 pipe, so the fraction of the SMs' issue
     # slots (SMs x 4 schedulers x clock x launch time) it fills says more than flops / peak.  ncu measures it directly for the

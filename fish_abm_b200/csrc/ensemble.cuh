@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             const float fdir = s_c0[f].x;
             const bool exotic = fabsf(fdir) >= 540.f;
             const int cxf = k1.w / a.ny, cyf = k1.w % a.ny;
+            const float ysh = yframe_shift(cyf), fyf = F.y + ysh;   // the pair arithmetic's y frame (kernels.cuh)
             PairAccR P;
             pair_acc_clear(P);
             for (int j0 = 0; j0 < n; j0 += 32) {
@@ -96,10 +97,10 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
                 const bool live = valid && dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
                 if (!__any_sync(FULL, live)) continue;
                 // a lane without a pair gets a candidate beyond every radius (pair_round has no `live` predicate)
-                const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + (float)dcy * CELL_F : 3.0e17f;
-                auto raw = [&](float& rx, float& ry, int& kcode) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); };
+                const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
+                auto raw = [&](float& rx, float& ry, int& kcode, float&, float& fyr) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); fyr = F.y; };
                 auto ids = [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; };
-                pair_round<false>(live, exotic, F.x, F.y, F.z, F.w, fdir, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
+                pair_round<false>(live, exotic, F.x, fyf, F.z, F.w, fdir, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
             }
             const unsigned red[6] = {__reduce_add_sync(FULL, P.ax0), __reduce_add_sync(FULL, P.ay0), __reduce_add_sync(FULL, P.ax1),
                                      __reduce_add_sync(FULL, P.ay1), __reduce_add_sync(FULL, P.ax2), __reduce_add_sync(FULL, P.ay2)};

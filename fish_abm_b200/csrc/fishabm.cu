@@ -18,8 +18,8 @@
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
 
 #include "kernels.cuh"
-#include "neighbour_v2.cuh"
 #include "neighbour_v3.cuh"
+#include "neighbour_v4.cuh"
 #include "ensemble.cuh"
 
 using namespace fishk;
@@ -92,8 +92,8 @@ struct fishabm_ctx {
     bool have_state = false;
     bool pending_sample = false;  // sample() of step `step-1` not yet applied (it shares the next move's neighbour pass)
     bool stats_on = false;
-    int nb_variant = 3;  // neighbour kernel design: 3 = candidate-parallel, packed-half filter + branch-free pair round (default);
-                         // 2 = candidate-parallel, fp32 filter (FISHABM_NEIGHBOUR=v2); 1 = focal-parallel (FISHABM_NEIGHBOUR=v1)
+    int nb_variant = 4;  // neighbour kernel design: 4 = candidate-parallel, one window per vertical cell pair (default);
+                         // 3 = candidate-parallel, one window per cell (FISHABM_NEIGHBOUR=v3); 1 = focal-parallel (FISHABM_NEIGHBOUR=v1)
     uint64_t launches = 0;
     float last_ms = 0.f;
 
@@ -227,7 +227,7 @@ cudaError_t preload_kernels() {
     L((const void*)export_pass_kernel); L((const void*)feed_list_kernel); L((const void*)halo_refresh_kernel);
     L((const void*)in_zone_generic_kernel); L((const void*)index_by_id_kernel); L((const void*)ingest_incoming_kernel);
     L((const void*)ingest_kernel); L((const void*)neighbour_kernel<false>); L((const void*)neighbour_kernel<true>);
-    L((const void*)neighbour_kernel_v2<false>); L((const void*)neighbour_kernel_v2<true>); L((const void*)scan_finish_kernel);
+    L((const void*)neighbour_kernel_v4<false>); L((const void*)neighbour_kernel_v4<true>); L((const void*)scan_finish_kernel);
     L((const void*)neighbour_kernel_v3<false, false>); L((const void*)neighbour_kernel_v3<true, false>);
     L((const void*)neighbour_kernel_v3<false, true>); L((const void*)neighbour_kernel_v3<true, true>);
     L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
@@ -304,7 +304,7 @@ enum { PASS_COUNTS = 1, PASS_TURN = 2 };
 int split_for(const fishabm_ctx* ctx) {
     // fewer cells than resident warps (small or dense schools): split every cell's fish over several work items
     const int own_cells = ctx->g.own_c1 - ctx->g.own_c0;
-    int split = std::max(1, std::min(32, (2 * ctx->nb_grid * V2_WARPS) / std::max(1, own_cells)));
+    int split = std::max(1, std::min(32, (2 * ctx->nb_grid * V4_WARPS) / std::max(1, own_cells)));
     if (const char* sp = getenv("FISHABM_SPLIT")) split = std::max(1, std::min(32, atoi(sp)));
     return split;
 }
@@ -358,10 +358,10 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     } else {
         ctx->wc_parity ^= 1;
         a.split = split_for(ctx);
-        const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V2_WARPS));
-        if (ctx->nb_variant == 2) {
-            if (ctx->stats_on) neighbour_kernel_v2<true><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
-            else neighbour_kernel_v2<false><<<grid, V2_THREADS, V2_SMEM_BYTES, ctx->stream>>>(a);
+        const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V4_WARPS));
+        if (ctx->nb_variant == 4) {   // (its work items are cell PAIRS when split == 1: never more warps than cells / 2 would be needed, but idle warps exit at once)
+            if (ctx->stats_on) neighbour_kernel_v4<true><<<grid, V4_THREADS, V4_SMEM_BYTES, ctx->stream>>>(a);
+            else neighbour_kernel_v4<false><<<grid, V4_THREADS, V4_SMEM_BYTES, ctx->stream>>>(a);
         } else if (fuse) {
             if (ctx->stats_on) neighbour_kernel_v3<true, true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, *fuse);
             else neighbour_kernel_v3<false, true><<<grid, V3_THREADS, V3_SMEM_BYTES, ctx->stream>>>(a, *fuse);
@@ -827,8 +827,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     }
     if (ok && ens) A(cudaFuncSetAttribute(ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->ens_smem));
     if (ok) {
-        A(cudaFuncSetAttribute(neighbour_kernel_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
-        A(cudaFuncSetAttribute(neighbour_kernel_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V2_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM_BYTES));
+        A(cudaFuncSetAttribute(neighbour_kernel_v4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
         A(cudaFuncSetAttribute(neighbour_kernel_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3_SMEM_BYTES));
@@ -836,12 +836,12 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     }
     const char* variant = getenv("FISHABM_NEIGHBOUR");
     if (variant && strcmp(variant, "v1") == 0) c->nb_variant = 1;
-    if (variant && strcmp(variant, "v2") == 0) c->nb_variant = 2;
+    if (variant && strcmp(variant, "v3") == 0) c->nb_variant = 3;
     if (ok) {
         int per_sm = 0, sms = 0;
         A(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device));
-        static_assert(V2_WARPS == V3_WARPS && V2_THREADS == V3_THREADS, "the work split assumes the same CTA shape");
-        if (c->nb_variant == 2) A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v2<false>, V2_THREADS, V2_SMEM_BYTES));
+        static_assert(V4_WARPS == V3_WARPS && V4_THREADS == V3_THREADS, "the work split assumes the same CTA shape");
+        if (c->nb_variant == 4) A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v4<false>, V4_THREADS, V4_SMEM_BYTES));
         else A(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, neighbour_kernel_v3<false, true>, V3_THREADS, V3_SMEM_BYTES));
         c->nb_grid = std::max(1, per_sm) * std::max(1, sms);  // persistent: one resident wave
         int scan_per_sm = 0;

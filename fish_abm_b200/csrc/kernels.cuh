@@ -165,8 +165,10 @@ __device__ __forceinline__ void cell_xy(int c, int ny, int& cx, int& cy) {
 // evaluation fell inside a rounding band.  dx,dy are exact (offsets are fp32, cell shifts are multiples of 200).
 // Products and sums are kept unfused so the operation order is the reference's.
 // bit0 dist<15, bit1 dist<100, bit2 dist<200, bit3 angle<165, bit4 angle<90
+// kcode = (kx + 1) + 3 * (ky + 1): the candidate's cell is (kx, ky) cells away from the focal fish's, kx in -1..1, ky >= -10
+// (|ky| = 2 occurs when a warp stages a vertical pair of cells: neighbour_v4.cuh)
 __device__ __noinline__ unsigned exact_pair_bits(float oxi, float oyi, float dir_deg, float oxj, float oyj, int kcode) {
-    const double sx = (double)((kcode % 3) - 1) * 200.0, sy = (double)((kcode / 3) - 1) * 200.0;
+    const double sx = (double)(((kcode + 30) % 3) - 1) * 200.0, sy = (double)(((kcode + 30) / 3) - 11) * 200.0;
     const double x = __dadd_rn(__dsub_rn((double)oxj, (double)oxi), sx);
     const double y = __dadd_rn(__dsub_rn((double)oyj, (double)oyi), sy);
     double c, s;
@@ -197,6 +199,14 @@ __device__ __noinline__ float getangle_wrap_exotic(float beta_rad, float dir_raw
     if (a > 180.0) a -= 360.0;
     return (float)(a * (M_PI / 180.0));
 }
+
+// The y frame of the pair arithmetic.  A fish of an EVEN cell row computes its pair geometry in the frame of the cell row
+// above it: its own offset becomes RN(oy - 200) and a candidate `ky` rows away RN(qy + (ky - 1) * 200); a fish of an odd
+// row uses its own cell's frame (offset unchanged, candidates RN(qy + ky * 200)).  Either way |y| < 400 (one rounding of
+// <= 1.5e-5 per coordinate, inside the bands' budget), and a warp that owns the vertical cell pair (2p, 2p + 1) stages ONE
+// window for the fish of both cells (neighbour_v4.cuh).  Every kernel design and the ensemble kernel use this frame, so
+// that they stay bit-identical to each other.
+__device__ __forceinline__ float yframe_shift(int cy) { return (cy & 1) ? 0.f : -CELL_F; }
 
 // cell k (0..8) of the 3x3 stencil around cell c: x offset k%3-1, y offset k/3-1.  Owned cells of a slab always
 // have both x neighbours inside the local grid (the halo columns).
@@ -288,7 +298,8 @@ __device__ __forceinline__ void finish_focal(const NeighArgs& a, int idx, int4 k
 // One candidate pair, one lane: exact classification (with the fp64 re-check of borderline predicates), zone / front
 // counts, and the avoidance / alignment / attraction turn of the pair (fish_mod.cpp:316-351) added as fixed-point
 // cos/sin to the lane's partial sums.  (qx,qy) is the candidate already shifted into the focal cell's frame, (qc,qs) its
-// heading.  `raw(rx, ry, kcode)` yields the candidate's unshifted in-cell offset and its stencil code for the re-check;
+// heading.  `raw(rx, ry, kcode, fxr, fyr)` yields the candidate's unshifted in-cell offset and its stencil code for the
+// re-check, and overwrites (fxr, fyr) -- preset to (fx, fy) -- with the focal fish's unshifted offset where that differs;
 // `ids(my, nb)` yields the two fish ids for a tie draw.  Returns true when the pair was re-checked in fp64.
 // counts are packed two to a word (16 bits each: a lane sees at most 32 candidates per reduction, a warp 1024):
 //   c_far = n200 | front << 16 | ties << 27,  c_near = n100 | n15 << 16
@@ -332,9 +343,9 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
     // flags are computed once, as predicates, after it)
     float d_cls = d, ca_cls = ca;
     if (unc) {
-        float rx, ry; int kcode;
-        raw(rx, ry, kcode);
-        const unsigned bits = exact_pair_bits(fx, fy, fdir, rx, ry, kcode);
+        float rx, ry, fxr = fx, fyr = fy; int kcode;
+        raw(rx, ry, kcode, fxr, fyr);
+        const unsigned bits = exact_pair_bits(fxr, fyr, fdir, rx, ry, kcode);
         d_cls = (bits & 1u) ? 1.f : (bits & 2u) ? 50.f : (bits & 4u) ? 150.f : 300.f;   // dist < 15 / < 100 / < 200 / not
         ca_cls = !(bits & 8u) ? -1.f : (bits & 16u) ? 0.5f : -0.5f;                      // angle >= 165 / < 90 / in between
     }
@@ -484,6 +495,62 @@ __device__ __forceinline__ bool pair_round(bool live, bool exotic, float fx, flo
     return false;
 }
 
+// The round without its fallback branch (neighbour_kernel_v4): the SAME arithmetic as pair_round's fast path, accumulated
+// unconditionally; the return value says that this lane's pair needs the generic code (borderline predicate or tie draw).
+// The caller ORs it over all rounds of a focal fish and, if any lane raised it, throws the accumulators away and redoes
+// the fish's rounds with pair_round_generic -- the rare case costs a few rounds more, the common one loses the vote, the
+// branch and its reconvergence bookkeeping from every round.
+// if (p) { x += vx; y += vy; } as two predicated adds (left to itself the compiler selects vx / 0 and adds: twice the instructions)
+__device__ __forceinline__ void pred_add2(bool p, unsigned& x, unsigned& y, unsigned vx, unsigned vy) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q add.u32 %0, %0, %2;\n\t@q add.u32 %1, %1, %3;\n\t}"
+        : "+r"(x), "+r"(y) : "r"(vx), "r"(vy), "r"((unsigned)p));
+}
+template <bool PACK8>
+__device__ __forceinline__ bool pair_fast(float fx, float fy, float fc, float fs, float qx, float qy, float qc, float qs, PairAccR& A) {
+    const float dx = qx - fx, dy = qy - fy;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float dot = fmaf(fc, dx, fs * dy);
+    const float cross = fmaf(fc, dy, -fs * dx);
+    const float rinv = rsqrt_ftz(d2);          // d2 == 0 -> +inf -> d, ca = NaN -> no predicate below holds
+    const float d = d2 * rinv, ca = dot * rinv;
+    const float tb = fmaf(rinv, 1.0e-4f, 2.0e-6f);
+    const float d15 = d - 15.f, d200 = d - 200.f;
+    const float near_r = fminf(fminf(fabsf(d15), fabsf(d - 100.f)), fabsf(d200));
+    const float near_c = fminf(fabsf(ca - COS165_F), fabsf(ca));
+    const bool front = ca > 0.f;
+    const bool unc = near_r < BAND_R || near_c < tb || (fabsf(cross) * rinv < COLLINEAR_BAND && front);
+    const bool in15 = d < 15.f, in100 = d < 100.f, in200 = d < 200.f, vis = ca > COS165_F;
+    const bool inter = vis && in200;
+    const bool al = in100 && !in15;
+    const float crossA = fmaf(fc, qs, -fs * qc), dotA = fmaf(fc, qc, fs * qs);
+    const float beta = atan2_fast(al ? crossA : cross, al ? dotA : dot);
+    const bool tie = (in15 && beta == 0.f) || (al && fabsf(beta) >= PI_F);
+    const float t = in15 ? beta - copysignf(PI_F, beta) : beta;
+    const float ee = in15 ? d : (al ? d15 : d200);   // d - 0 / d - 15 / d - 200: the same values pair_round subtracts
+    const float kz = in15 ? 0.1f : 0.004f;
+    const float wgt = rcp_ftz(fmaf(kz * ee, ee, 2.f));
+    const float th = t * wgt;
+    float sn, cs;
+    __sincosf(th, &sn, &cs);
+    const unsigned vx = (unsigned)__float_as_int(cs + FIX_MAGIC), vy = (unsigned)__float_as_int(sn + FIX_MAGIC);
+    if (PACK8) {
+        unsigned inc = in100 ? 0x010100u : 0x010000u;
+        inc = in15 ? 0x010101u : inc;
+        if (inter) A.c_far += inc;
+        if (front && in200) A.c_far += 0x01000000u;
+    } else {
+        if (inter) A.c_far += 1u;
+        if (front && in200) A.c_far += 0x10000u;
+        unsigned near_inc = in100 ? 1u : 0u;
+        near_inc = in15 ? 0x10001u : near_inc;
+        if (inter) A.c_near += near_inc;
+    }
+    pred_add2(inter && in15, A.ax0, A.ay0, vx, vy);
+    pred_add2(inter && al, A.ax1, A.ay1, vx, vy);
+    pred_add2(inter && !in100, A.ax2, A.ay2, vx, vy);
+    return unc || (inter && tie);
+}
+
 // heading unit vector of a stored heading (degrees, fp32): THE one place it is computed, so that a state that went
 // through get_state / set_state continues bit-identically to one that stayed on the device
 // (a true division: multiplying by a rounded 1/180 would triple the error of the unit vector, which the bearing bands of
@@ -526,7 +593,7 @@ __device__ __forceinline__ void move_core(float4& r, float4& c0, int lag, int& c
 
 template <bool STATS>
 __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, const uint32_t* __restrict__ tj, int fill,
-                                              bool active, float fx, float fy, float fc, float fs, float dir_raw,
+                                              bool active, float fx, float fy, float fy_raw, float fc, float fs, float dir_raw,
                                               bool exotic, uint32_t my_id, const NeighArgs& a, FocalAcc& A) {
     if (!active) return;
     for (int k = 0; k < fill; ++k) {
@@ -551,8 +618,7 @@ __device__ __forceinline__ void process_batch(const float4* __restrict__ tile, c
         if (unc) {
             const uint32_t code = tj[k];
             const float4 raw = __ldg(&a.rec[code & 0x0FFFFFFFu]);
-            const float4 me = make_float4(fx, fy, 0.f, 0.f);
-            const unsigned b = exact_pair_bits(me.x, me.y, dir_raw, raw.x, raw.y, (int)(code >> 28));
+            const unsigned b = exact_pair_bits(fx, fy_raw, dir_raw, raw.x, raw.y, (int)(code >> 28));
             in15 = b & 1u; in100 = b & 2u; in200 = b & 4u; vis = b & 8u; front = b & 16u;
             if (STATS) A.rechk++;
         }
@@ -614,6 +680,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
     }
     float4* tile = s_tile + warp * NB_CAP;
     uint32_t* tj = s_tj + warp * NB_CAP;
+    const float ysh = yframe_shift(c % a.g.ny);
 
     for (int base = s0; base < e0; base += 32) {
         const int i = base + lane;
@@ -637,7 +704,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
         int fill = 0;
         for (int k = 0; k < 9; ++k) {
             const int ks = __shfl_sync(FULL, nb_s, k), ke = __shfl_sync(FULL, nb_e, k);
-            const float sx = (float)((k % 3) - 1) * CELL_F, sy = (float)((k / 3) - 1) * CELL_F;
+            const float sx = (float)((k % 3) - 1) * CELL_F, sy = (float)((k / 3) - 1) * CELL_F + ysh;
             for (int b = ks; b < ke;) {
                 const int m = min(ke - b, NB_CAP - fill);
                 for (int t = lane; t < m; t += 32) {
@@ -649,7 +716,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
                 fill += m; b += m;
                 if (fill == NB_CAP) {
                     __syncwarp();
-                    process_batch<STATS>(tile, tj, fill, active, me.x, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
+                    process_batch<STATS>(tile, tj, fill, active, me.x, me.y + ysh, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
                     fold_batch(A);
                     __syncwarp();
                     fill = 0;
@@ -657,7 +724,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbour_kernel(const NeighArgs a
             }
         }
         __syncwarp();
-        process_batch<STATS>(tile, tj, fill, active, me.x, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
+        process_batch<STATS>(tile, tj, fill, active, me.x, me.y + ysh, me.y, me.z, me.w, dir_raw, exotic, (uint32_t)c1.w, a, A);
         fold_batch(A);
         __syncwarp();
 

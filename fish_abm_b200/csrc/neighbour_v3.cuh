@@ -1,6 +1,6 @@
 // K4, third design (default): candidate-parallel neighbour kernel with a packed-half filter and a branch-free pair round.
 //
-// Same decomposition as the second design (neighbour_v2.cuh: one warp per focal cell, the 3x3 stencil staged once per cell
+// Same decomposition as the second design (one warp per focal cell, the 3x3 stencil staged once per cell
 // as a window of candidates in the focal cell's frame, active fish compacted into focal groups, a cheap conservative
 // filter that compacts survivors into a queue, the exact pair math on the survivors 32 at a time, warp REDUX per focal
 // fish, one epilogue lane per focal fish) with the instruction count cut where ncu put it (the kernel issues
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
             e0 = min(e0, s0 + len);
         }
         if (s0 == e0) continue;
+        const float ysh = yframe_shift(c % a.g.ny);   // the pair arithmetic's y frame (kernels.cuh)
 
         // ---- the stencil as one flattened run: per-cell ranges, exclusive prefix (lanes 0..8), total T
         int nb_s = 0, nb_n = 0;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                     r[kx] = far;   // (initialised: an undefined value would be carried, through local memory, across the ky iterations)
                     if (u[kx] < hi[kx]) r[kx] = __ldg(&a.rec[src[kx] + u[kx]]);
                 }
-                const float sy = (float)(ky - 1) * CELL_F;
+                const float sy = (float)(ky - 1) * CELL_F + ysh;
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const float sx = (float)(kx - 1) * CELL_F;
@@ -207,7 +208,8 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                 }
                 if (valid && !active && lane < take) a.aux[i] = 0u;
                 if (active) {
-                    const float4 me = a.rec[i];
+                    float4 me = a.rec[i];
+                    me.y += ysh;
                     const int slot = nf + __popc(amask & lt_mask);
                     S.frec[slot] = me; S.fdir[slot] = a.cold0[i].x; S.fidx[slot] = i;
                     const float hxs = fmaf(me.x, V3_HSCALE, -V3_HCENTRE * V3_HSCALE), hys = fmaf(me.y, V3_HSCALE, -V3_HCENTRE * V3_HSCALE);
@@ -260,11 +262,12 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                     const float fdir = S.fdir[f];
                     PairAccR P;
                     pair_acc_clear(P);
-                    auto raw_of = [&](int j, float& rx, float& ry, int& kcode) {
+                    auto raw_of = [&](int j, float& rx, float& ry, int& kcode, float& fyr) {
                         int src;
                         locate(b, j, src, kcode);
                         const float4 raw = __ldg(&a.rec[src]);
                         rx = raw.x; ry = raw.y;
+                        fyr = __ldg(&a.rec[S.fidx[f]]).y;
                     };
                     auto ids_of = [&](int j, uint32_t& my, uint32_t& nb) {
                         int src, k;
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
                         const float4 Q = S.win[j];
                         const bool unc = pair_round<true>(
                             q0 + lane < qn, exotic, F.x, F.y, F.z, F.w, fdir, Q.x, Q.y, Q.z, Q.w, a.seed, a.replicate, a.step_move,
-                            [&](float& rx, float& ry, int& kcode) { raw_of(j, rx, ry, kcode); },
+                            [&](float& rx, float& ry, int& kcode, float&, float& fyr) { raw_of(j, rx, ry, kcode, fyr); },
                             [&](uint32_t& my, uint32_t& nb) { ids_of(j, my, nb); }, P);
                         if (STATS) st_rechk += __popc(__ballot_sync(FULL, unc));
                     }
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(V3_THREADS, FISHABM_V3_MIN_CTAS) neighbour_ker
             if (lane < nf) {
                 const int idx = S.fidx[lane];
                 const int4 k1 = a.cold1[idx];
-                const float4 F = S.frec[lane];
+                const float4 F = a.rec[idx];   // (the unshifted offset: sample()'s food cell)
                 if (nbatch > 1) {
                     const int4 cc = S.cnt[lane];
                     finish_focal(a, idx, k1, F.x, F.y, cc.x, cc.y, cc.z, cc.w, &S.acc[lane][0], 0);

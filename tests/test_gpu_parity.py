@@ -358,18 +358,26 @@ def test_rechecked_pairs_are_rare_and_counted(q100):
     assert st["rechecked"] < 1e-3 * st["candidates"]
 
 
-def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
-    """the focal-parallel (v1), the candidate-parallel fp32-filter (v2) and the default (v3: packed-half filter, branch-free
-    pair round, raw-bit sums) neighbour kernels accumulate integers from the same per-pair arithmetic, so every output must be
-    identical, whatever the candidate order"""
-    n, w = 60_000, 8_000   # ~37 fish per cell on average, some cells above 64
-    d = synth.uniform_state(n, w, w, seed=131)
-    d["coords"][:5000] = (np.array([4100.0, 4100.0]) + np.random.default_rng(3).uniform(0, 180, (5000, 2))).astype(np.float32)  # a dense clump: >256 candidates
-    q = synth.tile_quality(q100, w, w)
+@pytest.mark.parametrize("case", ["dense", "sparse_odd_rows"])
+def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch, case):
+    """the focal-parallel (v1), the one-window-per-cell (v3) and the default (v4: one window per vertical cell pair, round
+    without a fallback branch) neighbour kernels accumulate integers from the same per-pair arithmetic in the same frame,
+    so every output must be identical, whatever the candidate order.
+    dense: ~37 fish per cell (v4 falls back from cell pairs to single cells) and a clump that needs several window batches;
+    sparse_odd_rows: ~14 fish per cell (cell pairs fit one window) in a 41 x 33 cell world (the last row of every column is
+    a single cell)"""
+    if case == "dense":
+        n, w, h = 60_000, 8_000, 8_000
+        d = synth.uniform_state(n, w, h, seed=131)
+        d["coords"][:5000] = (np.array([4100.0, 4100.0]) + np.random.default_rng(3).uniform(0, 180, (5000, 2))).astype(np.float32)  # a dense clump: >256 candidates
+    else:
+        n, w, h = 19_000, 8_200, 6_600
+        d = synth.uniform_state(n, w, h, seed=132)
+    q = synth.tile_quality(q100, w, h)
     res = []
-    for variant in ("v1", "v2", "v3"):
+    for variant in ("v1", "v3", "v4"):
         monkeypatch.setenv("FISHABM_NEIGHBOUR", variant)
-        S = School(n=n, w=w, h=w, seed=17)
+        S = School(n=n, w=w, h=h, seed=17)
         S.set_state(**d); S.set_quality(q)
         zc = S.zone_counts(); turn = S.social()[0]
         S.step(3)
@@ -381,7 +389,7 @@ def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch):
         for k in res[0][2]:
             assert np.array_equal(res[0][2][k], res[other][2][k]), k
         assert np.array_equal(res[0][3], res[other][3])
-    O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, w, q.copy(), seed=17)
+    O = Oracle(State(**{k: v.copy() for k, v in d.items()}), w, h, q.copy(), seed=17)
     ids = np.r_[np.arange(0, 5000, 97), np.arange(5000, n, 1021)].astype(np.int32)
     assert np.array_equal(res[2][0][ids], O.zone_counts(ids))
 
