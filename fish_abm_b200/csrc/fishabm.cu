@@ -324,7 +324,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.g = ctx->g;
     a.active_lag_max = active_lag_max; a.do_sample = do_sample ? 1 : 0;
     a.step_sample = step_sample; a.step_move = step_move; a.seed = ctx->p.seed; a.replicate = ctx->p.replicate0;
-    a.split = 1;
+    a.split = 1; a.single_cols = 0;
     a.model = ctx->model;
     a.work_counter = ctx->work_counter + ctx->wc_parity;            // the persistent kernel's two cell counters alternate:
     a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
@@ -359,7 +359,14 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
         ctx->wc_parity ^= 1;
         a.split = split_for(ctx);
         const int grid = std::min(ctx->nb_grid, cdiv(own_cells * a.split, V4_WARPS));
-        if (ctx->nb_variant == 4) {   // (its work items are cell PAIRS when split == 1: never more warps than cells / 2 would be needed, but idle warps exit at once)
+        if (ctx->nb_variant == 4) {
+            // work items are cell PAIRS when split == 1, except in the last columns: when the dispenser runs dry every warp
+            // still finishes its item, so the final `tail` items' worth of work per resident warp is handed out cell by cell
+            if (a.split == 1) {
+                static const double tail = getenv("FISHABM_PAIR_TAIL") ? atof(getenv("FISHABM_PAIR_TAIL")) : 2.0;
+                const int ncols = own_cells / ctx->g.ny;
+                a.single_cols = std::min(ncols, (int)std::ceil(tail * ctx->nb_grid * V4_WARPS / (double)ctx->g.ny));
+            }
             if (ctx->stats_on) neighbour_kernel_v4<true><<<grid, V4_THREADS, V4_SMEM_BYTES, ctx->stream>>>(a);
             else neighbour_kernel_v4<false><<<grid, V4_THREADS, V4_SMEM_BYTES, ctx->stream>>>(a);
         } else if (fuse) {

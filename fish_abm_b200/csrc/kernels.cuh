@@ -92,9 +92,11 @@ struct NeighArgs {
     uint32_t step_sample, step_move;
     uint64_t seed;
     uint32_t replicate;
-    int split;                   // v2: work items per cell (each takes a slice of the cell's fish): 1 when cells outnumber
+    int split;                   // work items per cell (each takes a slice of the cell's fish): 1 when cells outnumber
                                  // the resident warps, up to 32 for small or dense schools that would otherwise leave SMs idle
-    int* work_counter;           // work-item dispenser of the persistent (v2) kernel, zero at launch
+    int single_cols;             // v4, split == 1: the LAST `single_cols` owned columns are handed out cell by cell instead of as cell
+                                 // pairs (same arithmetic, half the item length: a shorter tail when the resident warps run dry)
+    int* work_counter;           // work-item dispenser of the persistent kernels, zero at launch
     int* work_counter_next;      // the other dispenser: cleared by this launch for the next one
     Model model;
 };

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
     const int ny = a.g.ny;
     const int col0 = a.g.own_c0 / ny, ncols = (a.g.own_c1 - a.g.own_c0) / ny;
     const int npc = (ny + 1) >> 1;                                // cell pairs per column (the last one is a single cell when ny is odd)
-    const int n_items = a.split > 1 ? ncols * ny * a.split : ncols * npc;
+    const int pair_items = (ncols - a.single_cols) * npc;        // split == 1: cell pairs first, the last columns cell by cell
+    const int n_items = a.split > 1 ? ncols * ny * a.split : pair_items + a.single_cols * ny;
     const __half2 r2h = __float2half2_rn(V4_R2H);
     const uint32_t r2h_bits = *reinterpret_cast<const uint32_t*>(&r2h);
     const int kx_l = lane % 3, ky_l = lane / 3;                  // this lane's window cell (lanes 0..11)
@@ -97,12 +98,16 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
         // ---- the item: cells (cx, cy0 .. cy0 + left - 1) and, when cells are split over several warps, a slice of the cell's fish
         int cx, cy0, left, sub = 0;
         if (a.split > 1) {
-            const int cell = t / a.split;
-            sub = t - cell * a.split;
-            cx = cell / ny; cy0 = cell - cx * ny; left = 1;
+            int cell;
+            cell_xy(t, a.split, cell, sub);
+            cell_xy(cell, ny, cx, cy0); left = 1;
+        } else if (t < pair_items) {
+            int p;
+            cell_xy(t, npc, cx, p);
+            cy0 = 2 * p; left = min(2, ny - cy0);
         } else {
-            cx = t / npc;
-            cy0 = 2 * (t - cx * npc); left = min(2, ny - cy0);
+            cell_xy(t - pair_items, ny, cx, cy0); left = 1;
+            cx += ncols - a.single_cols;
         }
         cx += col0;
         int nfc = left;                                           // cells whose fish this window serves: 2, or 1
@@ -157,30 +162,25 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                 const int fill = min(T - base, V4_WIN);
                 const int padded = (fill + 64) & ~63;   // at least one padding slot; slot V4_SLOTS - 1 is always padding
                 const float4 far = make_float4(V4_FAR_X, V4_FAR_Y, 1.f, 0.f);
-                // range-major copy: each window cell is a contiguous run of sorted records, shifted into the item's frame by a
-                // per-cell constant (the periodic minimum image).  Three cells (one row) at a time so that three loads are in
-                // flight; a cell with more than 32 fish in this batch takes the trailing loop.
+                // row-major copy: a window row is three cells = three contiguous runs of sorted records side by side in the slot
+                // space; a lane finds its slot's run with two compares and shifts the record into the item's frame (the periodic
+                // minimum image).  Two loads in flight per lane.
 #pragma unroll 1
                 for (int ky = 0; ky < nfc + 2; ++ky) {
-                    float4 r[3];
-                    int u[3], hi[3], src[3];
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int k = 3 * ky + kx;
-                        const int pk = S.run_pre[k];
-                        u[kx] = max(pk, base) + lane; hi[kx] = min(S.run_pre[k + 1], base + fill); src[kx] = S.run_start[k] - pk;
-                        r[kx] = far;   // (initialised: an undefined value would be carried, through local memory, across the ky iterations)
-                        if (u[kx] < hi[kx]) r[kx] = __ldg(&a.rec[src[kx] + u[kx]]);
-                    }
+                    const int p0 = S.run_pre[3 * ky], p1 = S.run_pre[3 * ky + 1], p2 = S.run_pre[3 * ky + 2], p3 = S.run_pre[3 * ky + 3];
+                    const int o0 = S.run_start[3 * ky] - p0, o1 = S.run_start[3 * ky + 1] - p1, o2 = S.run_start[3 * ky + 2] - p2;
+                    const int hi = min(p3, base + fill);
                     const float sy = (float)(ky - row0) * CELL_F;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const float sx = (float)(kx - 1) * CELL_F;
-                        if (u[kx] < hi[kx]) S.win[u[kx] - base] = make_float4(r[kx].x + sx, r[kx].y + sy, r[kx].z, r[kx].w);
-                        for (int v = u[kx] + 32; v < hi[kx]; v += 32) {
-                            const float4 q = __ldg(&a.rec[src[kx] + v]);
-                            S.win[v - base] = make_float4(q.x + sx, q.y + sy, q.z, q.w);
-                        }
+                    for (int u = max(p0, base) + lane; u < hi; u += 64) {
+                        const int v = u + 32;
+                        const bool two = v < hi;
+                        const int ou = u >= p2 ? o2 : (u >= p1 ? o1 : o0), ov = v >= p2 ? o2 : (v >= p1 ? o1 : o0);
+                        const float sxu = u >= p2 ? CELL_F : (u >= p1 ? 0.f : -CELL_F), sxv = v >= p2 ? CELL_F : (v >= p1 ? 0.f : -CELL_F);
+                        const float4 q = __ldg(&a.rec[ou + u]);
+                        float4 r = far;
+                        if (two) r = __ldg(&a.rec[ov + v]);
+                        S.win[u - base] = make_float4(q.x + sxu, q.y + sy, q.z, q.w);
+                        if (two) S.win[v - base] = make_float4(r.x + sxv, r.y + sy, r.z, r.w);
                     }
                 }
                 for (int j = fill + lane; j < padded; j += 32) S.win[j] = far;
@@ -255,17 +255,20 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                 }
                 for (int b = 0; b < nbatch; ++b) {
                     const int fill = (staged == b) ? min(T - b * V4_WIN, V4_WIN) : stage(b);
-                    for (int f = 0; f < nf; ++f) {
+                    // the group's fish of the item's first cell come first (fish are cell-sorted): two runs of fish, each with its own
+                    // range of filter steps (64 candidates each)
+                    for (int part = 0; part < 2; ++part) {
+                    const int f_lo = part ? nf0 : 0, f_hi = part ? nf : nf0;
+                    int st_b = 0, st_e = (fill + 63) >> 6;
+                    if (nbatch == 1) { st_b = part ? st_beg1 : 0; st_e = part ? st_end1 : st_end0; }
+                    for (int f = f_lo; f < f_hi; ++f) {
                         // ---- filter: two candidates per lane and step, packed fp16, conservative disc test
                         const uint4 M = S.fmeta[f];   // broadcast
                         const __half2 fx2 = *reinterpret_cast<const __half2*>(&M.x), fy2 = *reinterpret_cast<const __half2*>(&M.y);
-                        const int fc = f >= nf0 ? 1 : 0;   // which cell of the item the fish is in (0 for a single cell: mid == e0)
-                        int st = 0, st_end = (fill + 63) >> 6;
-                        if (nbatch == 1) { st = fc ? st_beg1 : 0; st_end = fc ? st_end1 : st_end0; }
                         int qn = 0;
-                        int slot = lane + (st << 6);
-#pragma unroll 2
-                        for (; st < st_end; ++st) {
+#pragma unroll
+                        for (int st = 0; st < V4_SLOTS / 64; ++st) {
+                            if (st < st_b || st >= st_e) continue;   // (warp-uniform)
                             const uint32_t cxb = S.hx[st * 32 + lane], cyb = S.hy[st * 32 + lane];
                             const __half2 dx = __hsub2(*reinterpret_cast<const __half2*>(&cxb), fx2);
                             const __half2 dy = __hsub2(*reinterpret_cast<const __half2*>(&cyb), fy2);
@@ -274,10 +277,9 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                             v4_setp_lt2(*reinterpret_cast<const uint32_t*>(&d2), r2h_bits, p0, p1);
                             const unsigned b0 = __ballot_sync(FULL, p0), b1 = __ballot_sync(FULL, p1);
                             const int n0 = __popc(b0);
-                            if (p0) S.queue[qn + __popc(b0 & lt_mask)] = (unsigned char)slot;
-                            if (p1) S.queue[qn + n0 + __popc(b1 & lt_mask)] = (unsigned char)(slot | 32);
+                            if (p0) S.queue[qn + __popc(b0 & lt_mask)] = (unsigned char)(lane + 64 * st);
+                            if (p1) S.queue[qn + n0 + __popc(b1 & lt_mask)] = (unsigned char)(lane + 64 * st + 32);
                             qn += n0 + __popc(b1);
-                            slot += 64;
                         }
                         S.queue[qn + lane] = (unsigned char)(V4_SLOTS - 1);   // pad the last round with the far-away slot
                         __syncwarp();
@@ -288,12 +290,14 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                         pair_acc_clear(P);
                         const bool exotic = any_exotic != 0u && __any_sync(FULL, (M.z & V4_META_EXOTIC) != 0u);   // (warp-uniform)
                         unsigned dirty = exotic ? 1u : 0u;
-                        if (!exotic) {
+                        if (!exotic && qn > 0) {
                             const unsigned char* qp = S.queue + lane;
-                            for (int q0 = 0; q0 < qn; q0 += 32, qp += 32) {
+                            int q0 = 0;
+                            do {
                                 const float4 Q = S.win[(int)*qp];
                                 if (pair_fast<true>(F.x, F.y, F.z, F.w, Q.x, Q.y, Q.z, Q.w, P)) dirty = 1u;
-                            }
+                                q0 += 32; qp += 32;
+                            } while (q0 < qn);
                         }
                         if (__any_sync(FULL, dirty != 0u)) {   // rare: redo this fish's rounds with the generic per-lane code
                             pair_acc_clear(P);
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                                         const float4 raw = __ldg(&a.rec[src]);
                                         rx = raw.x; ry = raw.y;
                                         const int ky = (k * 11) >> 5, kx = k - 3 * ky;   // k / 3, k % 3 for k < 12
-                                        kcode = kx + 3 * (ky - fc);                     // (kx - 1 + 1) + 3 * (ky - (1 + fc) + 1)
+                                        kcode = kx + 3 * (ky - part);                    // (kx - 1 + 1) + 3 * (ky - (1 + fc) + 1)
                                         fyr = __ldg(&a.rec[fi]).y;
                                     },
                                     [&](uint32_t& my, uint32_t& nb) {
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                                 S.mb.cnt[f] = o;
                             }
                         }
+                    }
                     }
                 }
                 // ---- epilogue, one focal fish per lane

@@ -25,5 +25,5 @@ for _ in range(20):   # L2-warm: no flush between steps (what a resident 1M-fish
     S.step(1); wt += S.last_step_ms(); a, b = S.last_neighbour_ms(); wn += a; wk += b
 print(f"  L2-warm: step {wt/20*1e3:.1f} us, neighbour launch {wn/wk*1e3:.1f} us")
 S.enable_phase_timing(True); S.step(10); ph = S.last_phase_ms(); S.enable_phase_timing(False); S.flush()
-print(f"lib={os.environ.get('FISHABM_LIB','default')} variant={os.environ.get('FISHABM_NEIGHBOUR','v3')} n={n}: step {tot/STEPS*1e3:.1f} us, neighbour launch {nb/k*1e3:.1f} us, "
+print(f"lib={os.environ.get('FISHABM_LIB','default')} variant={os.environ.get("FISHABM_NEIGHBOUR","v4")} n={n}: step {tot/STEPS*1e3:.1f} us, neighbour launch {nb/k*1e3:.1f} us, "
       f"phases/step (L2 warm) {({p: round(v/10*1e3,1) for p, v in ph.items() if p != 'steps'})}")
