@@ -85,22 +85,35 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             const float ysh = yframe_shift(cyf), fyf = F.y + ysh;   // the pair arithmetic's y frame (kernels.cuh)
             PairAccR P;
             pair_acc_clear(P);
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                const bool valid = j < n;
-                const int jj = valid ? j : f;
-                const float4 Q = s_rec[jj];
-                const int cj = s_c1[jj].w;
-                int dcx = cj / a.ny - cxf, dcy = cj % a.ny - cyf;
-                if (dcx > 1) dcx -= a.nx; else if (dcx < -1) dcx += a.nx;   // periodic minimum image in whole cells
-                if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
-                const bool live = valid && dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
-                if (!__any_sync(FULL, live)) continue;
-                // a lane without a pair gets a candidate beyond every radius (pair_round has no `live` predicate)
-                const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
-                auto raw = [&](float& rx, float& ry, int& kcode, float&, float& fyr) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); fyr = F.y; };
-                auto ids = [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; };
-                pair_round<false>(live, exotic, F.x, fyf, F.z, F.w, fdir, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
+            // pass 0: the branch-free round (pair_fast) on every 32-chunk of the school; a borderline pair, a tie or an exotic
+            // heading anywhere (rare) discards the sums and pass 1 redoes the fish with the generic per-lane code
+            unsigned dirty = exotic ? 1u : 0u;
+            for (int pass_no = exotic ? 1 : 0; pass_no < 2; ++pass_no) {
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < n;
+                    const int jj = valid ? j : f;
+                    const float4 Q = s_rec[jj];
+                    const int cj = s_c1[jj].w;
+                    int dcx = cj / a.ny - cxf, dcy = cj % a.ny - cyf;
+                    if (dcx > 1) dcx -= a.nx; else if (dcx < -1) dcx += a.nx;   // periodic minimum image in whole cells
+                    if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
+                    const bool live = valid && dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
+                    if (!__any_sync(FULL, live)) continue;
+                    // a lane without a pair gets a candidate beyond every radius (the round has no `live` predicate)
+                    const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
+                    if (pass_no == 0) {
+                        if (pair_fast<false>(F.x, fyf, F.z, F.w, qx, qy, Q.z, Q.w, P)) dirty = 1u;
+                    } else {
+                        auto raw = [&](float& rx, float& ry, int& kcode, float&, float& fyr) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); fyr = F.y; };
+                        auto ids = [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; };
+                        pair_round_generic<false>(live, F.x, fyf, F.z, F.w, fdir, exotic, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
+                    }
+                }
+                if (pass_no == 0) {
+                    if (!__any_sync(FULL, dirty != 0u)) break;
+                    pair_acc_clear(P);
+                }
             }
             const unsigned red[6] = {__reduce_add_sync(FULL, P.ax0), __reduce_add_sync(FULL, P.ay0), __reduce_add_sync(FULL, P.ax1),
                                      __reduce_add_sync(FULL, P.ay1), __reduce_add_sync(FULL, P.ax2), __reduce_add_sync(FULL, P.ay2)};

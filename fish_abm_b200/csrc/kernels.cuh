@@ -946,7 +946,13 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
     a.cold1[i] = c1;
 }
 
-__global__ void __launch_bounds__(256) update_kernel(const UpdateArgs a) {
+// 8 CTAs per SM (32 registers, a few spills): the kernel is bound by memory latency, and the warps in flight hide more of it
+// than the registers would save (measured at C3: 33 us against 40 us with 48 registers / 5 CTAs; loads hoisted above the
+// feeding-rank loop did not help)
+#ifndef FISHABM_UPDATE_MIN_CTAS
+#define FISHABM_UPDATE_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(256, FISHABM_UPDATE_MIN_CTAS) update_kernel(const UpdateArgs a) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const int total = a.cell_start[a.g.ncell];
     const int b1 = a.cell_start[a.g.own_c0], e2 = a.cell_start[a.g.own_c1];
