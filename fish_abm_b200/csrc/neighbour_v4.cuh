@@ -55,10 +55,12 @@ struct V4WarpSmem {
     float4 frec[V4_FMAX];                                  // focal fish in the item's frame: x, y, cos, sin
     uint4 fmeta[V4_FMAX];                                  // fp16 x pair, fp16 y pair, flags (exotic heading), sorted index
     int run_pre[16];                                       // exclusive prefix of the window cells' counts (3 per row, + total)
-    int run_start[12];                                     // first sorted index of each window cell
+    int run_off[12];                                       // sorted index of a window cell's fish = run_off[cell] + flat slot
+    float2 shift[12];                                      // what takes a record of that cell into the item's frame (periodic minimum image)
     unsigned char queue[V4_SLOTS + 32];                    // survivors of the filter, padded to a whole round with the far slot
 };
 constexpr size_t V4_SMEM_BYTES = sizeof(V4WarpSmem) * V4_WARPS;
+static_assert(4 * (V4_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs per SM: 228 KB of shared memory, 1 KB of it reserved per CTA");
 
 __device__ __forceinline__ uint32_t v4_pack_half2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
@@ -140,7 +142,13 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
             const int st_beg1 = __shfl_sync(FULL, pre, 3) >> 6;
             const int st_end1 = (T + 63) >> 6;
             __syncwarp();
-            if (lane < ncw) { S.run_pre[lane] = pre; S.run_start[lane] = nb_s; }
+            // y frame: window row ky holds cell row cy0 - 1 + ky; the frame's zero is the odd row of the pair
+            const int row0 = (cy0 & 1) ? 1 : 2;                   // window row of the cell row at offset 0
+            const float hcy = (cy0 & 1) ? 100.f : 0.f;            // centre of the fp16 y coordinates (|y - hcy| <= 400)
+            if (lane < ncw) {
+                S.run_pre[lane] = pre; S.run_off[lane] = nb_s - pre;
+                S.shift[lane] = make_float2((float)(kx_l - 1) * CELL_F, (float)(ky_l - row0) * CELL_F);
+            }
             if (lane == ncw) S.run_pre[ncw] = T;
             __syncwarp();
             int s0 = a.cell_start[c], e0 = a.cell_start[c + nfc];
@@ -150,9 +158,6 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                 s0 = min(e0, s0 + sub * len);
                 e0 = min(e0, s0 + len);
             }
-            // y frame: window row ky holds cell row cy0 - 1 + ky; the frame's zero is the odd row of the pair
-            const int row0 = (cy0 & 1) ? 1 : 2;                   // window row of the cell row at offset 0
-            const float hcy = (cy0 & 1) ? 100.f : 0.f;            // centre of the fp16 y coordinates (|y - hcy| <= 400)
             const int nbatch = (T + V4_WIN - 1) / V4_WIN;
             const int fmax = nbatch > 1 ? V4_FMAX_MB : V4_FMAX;
             int staged = -1;  // batch currently in the window
@@ -162,36 +167,36 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                 const int fill = min(T - base, V4_WIN);
                 const int padded = (fill + 64) & ~63;   // at least one padding slot; slot V4_SLOTS - 1 is always padding
                 const float4 far = make_float4(V4_FAR_X, V4_FAR_Y, 1.f, 0.f);
-                // row-major copy: a window row is three cells = three contiguous runs of sorted records side by side in the slot
-                // space; a lane finds its slot's run with two compares and shifts the record into the item's frame (the periodic
-                // minimum image).  Two loads in flight per lane.
-#pragma unroll 1
-                for (int ky = 0; ky < nfc + 2; ++ky) {
-                    const int p0 = S.run_pre[3 * ky], p1 = S.run_pre[3 * ky + 1], p2 = S.run_pre[3 * ky + 2], p3 = S.run_pre[3 * ky + 3];
-                    const int o0 = S.run_start[3 * ky] - p0, o1 = S.run_start[3 * ky + 1] - p1, o2 = S.run_start[3 * ky + 2] - p2;
-                    const int hi = min(p3, base + fill);
-                    const float sy = (float)(ky - row0) * CELL_F;
-                    for (int u = max(p0, base) + lane; u < hi; u += 64) {
-                        const int v = u + 32;
-                        const bool two = v < hi;
-                        const int ou = u >= p2 ? o2 : (u >= p1 ? o1 : o0), ov = v >= p2 ? o2 : (v >= p1 ? o1 : o0);
-                        const float sxu = u >= p2 ? CELL_F : (u >= p1 ? 0.f : -CELL_F), sxv = v >= p2 ? CELL_F : (v >= p1 ? 0.f : -CELL_F);
-                        const float4 q = __ldg(&a.rec[ou + u]);
-                        float4 r = far;
-                        if (two) r = __ldg(&a.rec[ov + v]);
-                        S.win[u - base] = make_float4(q.x + sxu, q.y + sy, q.z, q.w);
-                        if (two) S.win[v - base] = make_float4(r.x + sxv, r.y + sy, r.z, r.w);
-                    }
-                }
-                for (int j = fill + lane; j < padded; j += 32) S.win[j] = far;
-                if (lane == 0) S.win[V4_SLOTS - 1] = far;
-                __syncwarp();
-                // the same coordinates as packed fp16 pairs for the filter: element 32*s + l = candidates (64*s + l, 64*s + 32 + l)
+                // flat copy, 64 slots per pass (two per lane, the pair the filter reads as one fp16x2 word): the window's cells are
+                // contiguous runs of sorted records side by side in the slot space; a lane finds its slots' cells by counting
+                // the cell boundaries inside the pass's span (one or two, read as broadcasts), loads the records, shifts them
+                // into the item's frame and writes them as fp32 (rounds) and as packed fp16 pairs (filter)
+                int kc = 0;                              // cell of the first slot of the pass (the same in every lane)
                 for (int j0 = 0; j0 < padded; j0 += 64) {
-                    const float2 p = *reinterpret_cast<const float2*>(&S.win[j0 + lane]), q = *reinterpret_cast<const float2*>(&S.win[j0 + 32 + lane]);
-                    S.hx[(j0 >> 1) + lane] = v4_pack_half2(fmaf(p.x, V4_HSCALE, -V4_HCX * V4_HSCALE), fmaf(q.x, V4_HSCALE, -V4_HCX * V4_HSCALE));
-                    S.hy[(j0 >> 1) + lane] = v4_pack_half2((p.y - hcy) * V4_HSCALE, (q.y - hcy) * V4_HSCALE);
+                    const int u = base + j0 + lane, v = u + 32;
+                    int ku = kc, kv = kc;
+                    for (int m = kc + 1; m < ncw; ++m) {
+                        const int pm = S.run_pre[m];
+                        if (pm > base + j0 + 63) break;
+                        ku += (u >= pm) ? 1 : 0; kv += (v >= pm) ? 1 : 0;
+                    }
+                    float4 q = far, r = far;
+                    if (j0 + lane < fill) {
+                        q = __ldg(&a.rec[S.run_off[ku] + u]);
+                        const float2 sh = S.shift[ku];
+                        q.x += sh.x; q.y += sh.y;
+                    }
+                    if (j0 + 32 + lane < fill) {
+                        r = __ldg(&a.rec[S.run_off[kv] + v]);
+                        const float2 sh = S.shift[kv];
+                        r.x += sh.x; r.y += sh.y;
+                    }
+                    S.win[j0 + lane] = q; S.win[j0 + 32 + lane] = r;
+                    S.hx[(j0 >> 1) + lane] = v4_pack_half2(fmaf(q.x, V4_HSCALE, -V4_HCX * V4_HSCALE), fmaf(r.x, V4_HSCALE, -V4_HCX * V4_HSCALE));
+                    S.hy[(j0 >> 1) + lane] = v4_pack_half2((q.y - hcy) * V4_HSCALE, (r.y - hcy) * V4_HSCALE);
+                    kc = __shfl_sync(FULL, kv, 31);
                 }
+                if (lane == 0) S.win[V4_SLOTS - 1] = far;
                 __syncwarp();
                 staged = b;
                 return fill;
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                 k = 0;
 #pragma unroll
                 for (int m = 1; m < 12; ++m) k += (m < ncw && u >= S.run_pre[m]) ? 1 : 0;
-                src = S.run_start[k] + u - S.run_pre[k];
+                src = S.run_off[k] + u;
             };
 
             int pos = s0;
