@@ -402,9 +402,9 @@ def ours(args, rank: int, world: int, local_rank: int):
                 "traffic_note": "ncu dram__bytes_read+write of one launch (the 1M-fish state is L2-resident: 16 B x 1M hot records)" if cap else None,
                 "issue_slots": issue,
                 "ncu": {k: cap[k] for k in ("duration", "issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct", "warp_instructions", "threads_per_instruction", "registers", "source") if k in cap} if cap else None,
-                "binding_limit": "instruction issue (85 % of the issue slots are used): an interacting pair costs ~115 issued instructions per 32 pairs "
+                "binding_limit": "instruction issue (85 % of the issue slots are used): a round of 32 pairs costs ~100 issued instructions "
                                  "(geometry, rounding bands, polynomial atan2, weight, MUFU sin/cos, fixed-point sums) of which SURVEY 8(d)'s convention counts "
-                                 "20 flops, and a candidate ~0.4 (packed-fp16 disc filter) of which it counts 13; see DESIGN.md section 3",
+                                 "20 flops per interacting pair, and a candidate ~0.4 (packed-fp16 disc filter) of which it counts 13; see DESIGN.md section 3",
                 "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock); FP32 is not in MEASURED_PEAKS.json",
                 "flops_per_launch": flops_alg(cand, inter), "candidates_per_launch": cand, "interacting_per_launch": inter,
                 "focal_per_launch": focal, "launch_ms": per_launch_ms, "share_of_step": nb_ms / total_ms}

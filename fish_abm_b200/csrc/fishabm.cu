@@ -48,6 +48,8 @@ struct fishabm_ctx {
     fishabm_params p;
     std::string err_msg;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // get_state: downloads that overlap the pending sample() pass
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> nb_events;  // around each neighbour kernel of the last call
     int nb_events_used = 0;
@@ -787,6 +789,8 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
         A(cudaMemcpyToSymbol(g_unit_deg, tab, sizeof tab));
     }
     A(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     A(cudaEventCreate(&c->ev0)); A(cudaEventCreate(&c->ev1));
     for (int k = 0; k < (ens ? 1 : 2) && ok; ++k) {
         A(dalloc(&c->buf[k].rec, cap)); A(dalloc(&c->buf[k].cold0, cap)); A(dalloc(&c->buf[k].cold1, cap)); A(dalloc(&c->buf[k].cell, cap));
@@ -887,6 +891,8 @@ void fishabm_destroy(fishabm_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     free(c->h_q8);
     delete c;
 }
@@ -1063,10 +1069,29 @@ int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* spe
         CK(cudaStreamSynchronize(s));
         return 0;
     }
-    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
+    cudaStream_t s = ctx->stream;
+    // A pending sample() (fishabm_step leaves the last one to the next neighbour pass) changes neither positions nor headings
+    // nor speeds (fish_mod.cpp:540-586 writes lag, sample_rate, food_intake, speed_factor): those three arrays -- 32 of the 52
+    // bytes per fish -- are exported first and travel to the host on a second stream WHILE the pending pass runs.
+    const bool early = ctx->pending_sample && !ctx->slab && (coords || dir || speed);
+    if (early) {
+        const Buffers& b0 = ctx->buf[ctx->cur];
+        ExportArgs e{b0.rec, b0.cold0, b0.cold1, b0.cell, ctx->cell_start, coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr,
+                     speed ? ctx->st_speed : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->g, 0};
+        export_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(e);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_copy, s));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        const size_t n = (size_t)ctx->n;
+        if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (speed) CK(cudaMemcpyAsync(speed, ctx->st_speed, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        coords = nullptr; dir = nullptr; speed = nullptr;   // done: the second export below leaves them out
+    }
+    { int rcf = flush_pending(ctx); if (rcf) { if (early) cudaStreamSynchronize(ctx->copy_stream); return rcf; } }
     int cnt = 0;
     if ((rc = owned_range(ctx, &cnt))) return rc;
-    cudaStream_t s = ctx->stream;
     const Buffers& b = ctx->buf[ctx->cur];
     ExportArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start,
                  coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr, speed ? ctx->st_speed : nullptr,
@@ -1075,6 +1100,10 @@ int fishabm_get_state(fishabm_ctx* ctx, double* coords, double* dir, double* spe
     if (cnt > 0) export_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
+    struct CopyGuard {   // whatever happens below, the early downloads have landed before the call returns
+        fishabm_ctx* c; bool on;
+        ~CopyGuard() { if (on) cudaStreamSynchronize(c->copy_stream); }
+    } guard{ctx, early};
     if ((rc = fetch_ids(ctx, cnt))) return rc;
     if ((rc = fetch(ctx, coords, ctx->st_coords, cnt, 2))) return rc;
     if ((rc = fetch(ctx, dir, ctx->st_dir, cnt, 1))) return rc;
