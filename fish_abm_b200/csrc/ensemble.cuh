@@ -1,6 +1,7 @@
 // K8: replicate ensembles (BASELINE.json configs[4]: 65,536 schools of N=200).  One CTA owns one school for the whole
-// launch: the school's state and its food grid live in shared memory, every step is an all-pairs neighbour pass
-// (a warp per focal fish, candidates across the lanes) followed by the per-fish update, and only the logged
+// launch: the school's state and its food grid live in shared memory, every step is a neighbour pass over all pairs of the
+// school (a warp per focal fish: a cheap in-range filter over all fish compacts the few that can interact into a queue,
+// the pair math runs on those, 32 at a time) followed by the per-fish update, and only the logged
 // observables (sum of the food grid per step, food_intake every k steps: the reference's commented-out loggers,
 // fish_mod.cpp:132-141,149-154) touch HBM in between.  Replicates never communicate; the per-pair arithmetic, the
 // per-focal epilogue and the move arithmetic are the SAME device functions the cell-list path uses (pair_math,
@@ -19,7 +20,7 @@ enum { ENS_OP_STEPS = 0, ENS_OP_MOVE = 1, ENS_OP_SAMPLE = 2, ENS_OP_QUERY = 3 };
 struct EnsembleArgs {
     float4* rec;      // [R][n]  in-cell offset + heading unit vector
     float4* cold0;    // [R][n]  dir, speed, speed_factor, -
-    int4* cold1;      // [R][n]  lag, sample_rate, food_intake, cell (cx*ny+cy)
+    int4* cold1;      // [R][n]  lag, sample_rate, food_intake, cell (cx << 16 | cy)
     uint8_t* quality; // [R][qrows*qcols]
     int n, nx, ny, qcols, qcells;
     int replicates;
@@ -36,9 +37,12 @@ struct EnsembleArgs {
     const Model* models;  // [R]: every replicate has its own model constants (parameter sweeps, BASELINE.json configs[4])
 };
 
+__host__ __device__ inline int ens_queue_stride(int n) { return (n + 32 + 7) & ~7; }   // survivor queue of one warp, 16-bit entries
 __host__ __device__ inline size_t ensemble_smem_bytes(int n, int qcells) {
-    return (size_t)n * (16 + 16 + 16 + 16 + 4 + 4 + 4 + 4) + (size_t)((qcells + 15) / 16) * 16 + 64;
+    return (size_t)n * (16 + 16 + 16 + 16 + 4 + 4 + 4 + 4) + (size_t)((qcells + 15) / 16) * 16 + 64 +
+           (size_t)(ENS_THREADS / 32) * ens_queue_stride(n) * 2;
 }
+__device__ __forceinline__ int ens_cell_pack(int cx, int cy) { return (cx << 16) | cy; }
 
 __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const EnsembleArgs a) {
     extern __shared__ __align__(16) unsigned char ens_smem[];
@@ -54,6 +58,8 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
     int* s_updv = s_updq + n;
     uint8_t* s_q = reinterpret_cast<uint8_t*>(s_updv + n);
     int* s_total = reinterpret_cast<int*>(s_q + ((a.qcells + 15) / 16) * 16);
+    int* s_dens = s_total + 4;   // [0] interacting pairs and [1] focal fish of the running pass, [2] the next pass goes direct
+    unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_total + 16) + (size_t)warp * ens_queue_stride(n);
 
     const int rep = blockIdx.x;
     const uint32_t replicate = a.replicate0 + (uint32_t)rep;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
     const size_t base = (size_t)rep * n;
     for (int i = tid; i < n; i += ENS_THREADS) { s_rec[i] = a.rec[base + i]; s_c0[i] = a.cold0[base + i]; s_c1[i] = a.cold1[base + i]; }
     const uint8_t* gq = a.quality + (size_t)rep * a.qcells;
-    if (tid == 0) *s_total = 0;
+    if (tid == 0) { *s_total = 0; s_dens[0] = 0; s_dens[1] = 0; s_dens[2] = 0; }
     __syncthreads();
     {
         int part = 0;
@@ -72,8 +78,25 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
     }
     __syncthreads();
 
-    // ---- neighbour pass: all pairs of the school, a warp per focal fish ------------------------------------------
+    // ---- neighbour pass: a warp per focal fish ------------------------------------------------------------------------
+    // candidate j seen from focal fish f: the periodic minimum image in whole cells, then the SAME frame arithmetic as the
+    // cell-list kernels (kernels.cuh: yframe_shift)
+    auto image = [&](int cj, int cxf, int cyf, int& dcx, int& dcy) {
+        dcx = (cj >> 16) - cxf; dcy = (cj & 0xFFFF) - cyf;
+        if (dcx > 1) dcx -= a.nx; else if (dcx < -1) dcx += a.nx;
+        if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
+        return dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
+    };
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // Two ways through the school's fish, bit-identical in their results (integer sums of the same per-pair arithmetic):
+    //   filtered  every fish against the interaction range first, in the round's own fp32 arithmetic (the same dx, dy, d2 bits, so
+    //             the cut can sit right behind the 200-unit band); the survivors are compacted into the warp's queue and only
+    //             they go through the pair rounds -- a dispersed school has a handful per fish;
+    //   direct    the rounds take all fish, 32 at a time -- a cohesive school (the reference's lattice start stays one:
+    //             BASELINE.json configs[4]) has nearly every pair in range, and the filter would only add to the work.
+    // Which one a pass uses follows the interacting fraction the PREVIOUS pass of this school counted (s_dens).
     auto pass = [&](int active_lag_max, int do_sample, uint32_t step_sample, uint32_t step_move) {
+        const bool direct = s_dens[2] != 0;
         for (int f = warp; f < n; f += ENS_THREADS / 32) {
             const int4 k1 = s_c1[f];
             const bool active = active_lag_max < 0 || k1.x <= active_lag_max;
@@ -81,26 +104,44 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             const float4 F = s_rec[f];
             const float fdir = s_c0[f].x;
             const bool exotic = fabsf(fdir) >= 540.f;
-            const int cxf = k1.w / a.ny, cyf = k1.w % a.ny;
+            const int cxf = k1.w >> 16, cyf = k1.w & 0xFFFF;
             const float ysh = yframe_shift(cyf), fyf = F.y + ysh;   // the pair arithmetic's y frame (kernels.cuh)
-            PairAccR P;
-            pair_acc_clear(P);
-            // pass 0: the branch-free round (pair_fast) on every 32-chunk of the school; a borderline pair, a tie or an exotic
-            // heading anywhere (rare) discards the sums and pass 1 redoes the fish with the generic per-lane code
-            unsigned dirty = exotic ? 1u : 0u;
-            for (int pass_no = exotic ? 1 : 0; pass_no < 2; ++pass_no) {
+            int count = n;   // entries the rounds go through: all fish (direct) or the queue's survivors
+            if (!direct) {
+                int qn = 0;
+                __syncwarp();
                 for (int j0 = 0; j0 < n; j0 += 32) {
                     const int j = j0 + lane;
-                    const bool valid = j < n;
-                    const int jj = valid ? j : f;
+                    bool keep = false;
+                    if (j < n) {
+                        const float2 q = *reinterpret_cast<const float2*>(&s_rec[j]);
+                        int dcx, dcy;
+                        if (image(s_c1[j].w, cxf, cyf, dcx, dcy)) {
+                            const float dx = (q.x + (float)dcx * CELL_F) - F.x, dy = (q.y + ((float)dcy * CELL_F + ysh)) - fyf;
+                            keep = fmaf(dx, dx, dy * dy) < (CELL_F + 2.f * BAND_R) * (CELL_F + 2.f * BAND_R);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) s_queue[qn + __popc(m & lt_mask)] = (unsigned short)j;
+                    qn += __popc(m);
+                }
+                __syncwarp();
+                count = qn;
+            }
+            PairAccR P;
+            pair_acc_clear(P);
+            // pass 0: the branch-free round (pair_fast); a borderline pair, a tie or an exotic heading anywhere (rare) discards
+            // the sums and pass 1 redoes the fish with the generic per-lane code.  A lane without a pair gets a candidate beyond
+            // every radius (the round has no `live` predicate).
+            unsigned dirty = exotic ? 1u : 0u;
+            for (int pass_no = exotic ? 1 : 0; pass_no < 2; ++pass_no) {
+                for (int q0 = 0; q0 < count; q0 += 32) {
+                    const int e = q0 + lane;
+                    const int jj = e < count ? (direct ? e : (int)s_queue[e]) : f;
                     const float4 Q = s_rec[jj];
-                    const int cj = s_c1[jj].w;
-                    int dcx = cj / a.ny - cxf, dcy = cj % a.ny - cyf;
-                    if (dcx > 1) dcx -= a.nx; else if (dcx < -1) dcx += a.nx;   // periodic minimum image in whole cells
-                    if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
-                    const bool live = valid && dcx >= -1 && dcx <= 1 && dcy >= -1 && dcy <= 1;
-                    if (!__any_sync(FULL, live)) continue;
-                    // a lane without a pair gets a candidate beyond every radius (the round has no `live` predicate)
+                    int dcx, dcy;
+                    const bool live = image(s_c1[jj].w, cxf, cyf, dcx, dcy) && e < count;
+                    if (direct && !__any_sync(FULL, live)) continue;
                     const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
                     if (pass_no == 0) {
                         if (pair_fast<false>(F.x, fyf, F.z, F.w, qx, qy, Q.z, Q.w, P)) dirty = 1u;
@@ -126,7 +167,13 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
                 const FocalResult r = focal_result(model, a.seed, replicate, step_sample, step_move, do_sample, (uint32_t)f, k1.x, k1.y, F.x, F.y,
                                                    c15, c100, c200, cfr, sums, ties);
                 s_cnt[f] = r.cnt; s_turn[f] = r.turn; s_aux[f] = r.aux;
+                atomicAdd(&s_dens[0], c200); atomicAdd(&s_dens[1], 1);
             }
+        }
+        __syncthreads();
+        if (tid == 0) {   // the next pass goes direct when more than half of all pairs interacted in this one
+            s_dens[2] = (2 * s_dens[0] > s_dens[1] * n) ? 1 : 0;
+            s_dens[0] = 0; s_dens[1] = 0;
         }
         __syncthreads();
     };
@@ -151,8 +198,8 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
                         }
                     }
                     const int fl = (int)((aux >> AUX_FOOD_SHIFT) & AUX_FOOD_MASK);
-                    const int gx = (c1.w / a.ny) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
-                    const int gy = (c1.w % a.ny) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
+                    const int gx = (c1.w >> 16) * FOOD_PER_CELL + fl % FOOD_PER_CELL;
+                    const int gy = (c1.w & 0xFFFF) * FOOD_PER_CELL + fl / FOOD_PER_CELL;
                     const int qi = gy * a.qcols + gx;
                     const int q = (int)s_q[qi];
                     if (rank < q) { c0.z = model.fed_sf; c1.z += 1; c1.y = model.rate_fed; atomicSub(s_total, 1); }
@@ -164,12 +211,12 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             if (do_move) {  // move(), fish_mod.cpp:165-179
                 const int err = fishrng::draw(a.seed, replicate, step_move, (uint32_t)i, STREAM_ERROR, 0, -model.error_range, model.error_range);
                 float4 r = s_rec[i];
-                int cx = c1.w / a.ny, cy = c1.w % a.ny;
+                int cx = c1.w >> 16, cy = c1.w & 0xFFFF;
                 const bool moving = c1.x == 0;
                 move_core(r, c0, c1.x, cx, cy, moving ? s_turn[i] : 0.f, moving ? s_cnt[i].w : 0, err, a.rolling, (float)(2.0 / a.speed_norm));
                 cx %= a.nx; if (cx < 0) cx += a.nx;
                 cy %= a.ny; if (cy < 0) cy += a.ny;
-                c1.w = cx * a.ny + cy;
+                c1.w = ens_cell_pack(cx, cy);
                 s_rec[i] = r;
             }
             s_c0[i] = c0;
@@ -245,7 +292,7 @@ __global__ void ens_ingest_kernel(const EnsIoArgs a) {
     heading_vector(dirf, cs, sn);
     a.rec[i] = make_float4(ox, oy, cs, sn);
     a.cold0[i] = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
-    a.cold1[i] = make_int4(a.lag[i], a.rate[i], a.intake[i], cx * a.ny + cy);
+    a.cold1[i] = make_int4(a.lag[i], a.rate[i], a.intake[i], ens_cell_pack(cx, cy));
 }
 __global__ void ens_export_kernel(const EnsIoArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,8 +300,8 @@ __global__ void ens_export_kernel(const EnsIoArgs a) {
     const float4 r = a.rec[i], c0 = a.cold0[i];
     const int4 c1 = a.cold1[i];
     if (a.coords) {
-        a.coords[2 * i] = (double)(c1.w / a.ny) * CELL_I + (double)r.x;
-        a.coords[2 * i + 1] = (double)(c1.w % a.ny) * CELL_I + (double)r.y;
+        a.coords[2 * i] = (double)(c1.w >> 16) * CELL_I + (double)r.x;
+        a.coords[2 * i + 1] = (double)(c1.w & 0xFFFF) * CELL_I + (double)r.y;
     }
     if (a.dir) a.dir[i] = (double)c0.x;
     if (a.speed) a.speed[i] = (double)c0.y;
