@@ -365,7 +365,8 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
             // work items are cell PAIRS when split == 1, except in the last columns: when the dispenser runs dry every warp
             // still finishes its item, so the final `tail` items' worth of work per resident warp is handed out cell by cell
             if (a.split == 1) {
-                static const double tail = getenv("FISHABM_PAIR_TAIL") ? atof(getenv("FISHABM_PAIR_TAIL")) : 2.0;
+                const char* pt = getenv("FISHABM_PAIR_TAIL");   // (tests force 0: every column as cell pairs, however small the school)
+                const double tail = pt ? atof(pt) : 2.0;
                 const int ncols = own_cells / ctx->g.ny;
                 a.single_cols = std::min(ncols, (int)std::ceil(tail * ctx->nb_grid * V4_WARPS / (double)ctx->g.ny));
             }

@@ -427,7 +427,7 @@ def run_slab_bench(args, rank: int, world: int, local_rank: int):
                 "clocks": clk, "gpu_launches": int(cs[3]),
                 "e2e": {"value": n * e2e_steps / e2e_max, "unit": "agent-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h) + 8 * world,
                         "steps": e2e_steps, "api": "per rank: fishabm_set_state_owned(its fish, pinned host arrays) + halo exchange + fishabm_step(1) + fishabm_get_state_owned + fishabm_sum_quality"},
-                "roofline": {"bound": "fp32", "kernel": "neighbour_kernel_v3", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "roofline": {"bound": "fp32", "kernel": "neighbour_kernel_v4", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                              "frac": achieved / fp32_peak, "traffic": None, "per": "rank (slowest rank's launch time, mean rank's pairs)",
                              "peak_source": f"SMs({sm_count}) x 128 lanes x 2 x sm_max_mhz ({how} clock)", "flops_per_launch": flops,
                              "launch_ms": per_launch_ms, "share_of_step": float(cm[4]) / main["ms_max"]},

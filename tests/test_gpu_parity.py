@@ -375,15 +375,18 @@ def test_kernel_designs_agree_bit_for_bit(q100, monkeypatch, case):
         d = synth.uniform_state(n, w, h, seed=132)
     q = synth.tile_quality(q100, w, h)
     res = []
-    for variant in ("v1", "v3", "v4"):
+    for variant in ("v1", "v3", "v4", "v4-pairs-only"):
         monkeypatch.setenv("FISHABM_NEIGHBOUR", variant)
+        if variant == "v4-pairs-only":   # a school this small would be split cell by cell over the warps: force whole cell pairs
+            monkeypatch.setenv("FISHABM_SPLIT", "1")
+            monkeypatch.setenv("FISHABM_PAIR_TAIL", "0")
         S = School(n=n, w=w, h=h, seed=17)
         S.set_state(**d); S.set_quality(q)
         zc = S.zone_counts(); turn = S.social()[0]
         S.step(3)
         res.append((zc, turn, S.get_state(), S.get_quality()))
         S.close()
-    for other in (1, 2):
+    for other in (1, 2, 3):
         assert np.array_equal(res[0][0], res[other][0])
         assert np.array_equal(res[0][1], res[other][1])
         for k in res[0][2]:
