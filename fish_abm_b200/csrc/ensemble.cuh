@@ -95,6 +95,11 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
     //   direct    the rounds take all fish, 32 at a time -- a cohesive school (the reference's lattice start stays one:
     //             BASELINE.json configs[4]) has nearly every pair in range, and the filter would only add to the work.
     // Which one a pass uses follows the interacting fraction the PREVIOUS pass of this school counted (s_dens).
+    // The shift that takes candidate j into focal fish f's frame depends only on the two fish's cells.  In a world of at most
+    // 32 x 32 cells (6400 units; the default school lives in 10 x 10) every lane holds the shift of ONE cell column and ONE cell
+    // row of the focal fish -- (column - cxf) * 200 wrapped to the nearest image, or a far-away value when the image is not
+    // adjacent -- and a pair costs two shuffles instead of the wrap arithmetic.  Larger worlds compute it per pair.
+    const bool lut_ok = a.nx <= 32 && a.ny <= 32;
     auto pass = [&](int active_lag_max, int do_sample, uint32_t step_sample, uint32_t step_move) {
         const bool direct = s_dens[2] != 0;
         for (int f = warp; f < n; f += ENS_THREADS / 32) {
@@ -106,21 +111,37 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             const bool exotic = fabsf(fdir) >= 540.f;
             const int cxf = k1.w >> 16, cyf = k1.w & 0xFFFF;
             const float ysh = yframe_shift(cyf), fyf = F.y + ysh;   // the pair arithmetic's y frame (kernels.cuh)
+            float lutx = 1.0e18f, luty = 3.0e17f;                   // this lane's cell column / row seen from the focal fish
+            if (lut_ok) {
+                int dcx = lane - cxf, dcy = lane - cyf;
+                if (dcx > 1) dcx -= a.nx; else if (dcx < -1) dcx += a.nx;
+                if (dcy > 1) dcy -= a.ny; else if (dcy < -1) dcy += a.ny;
+                if (lane < a.nx && dcx >= -1 && dcx <= 1) lutx = (float)dcx * CELL_F;
+                if (lane < a.ny && dcy >= -1 && dcy <= 1) luty = (float)dcy * CELL_F + ysh;
+            }
+            // the candidate's shift into the focal frame: (sx, sy), far away unless its cell image is adjacent
+            auto shift_of = [&](int cj, float& sx, float& sy) {
+                if (lut_ok) {
+                    sx = __shfl_sync(FULL, lutx, cj >> 16);
+                    sy = __shfl_sync(FULL, luty, cj & 0xFFFF);
+                } else {
+                    int dcx, dcy;
+                    const bool inr = image(cj, cxf, cyf, dcx, dcy);
+                    sx = inr ? (float)dcx * CELL_F : 1.0e18f;
+                    sy = inr ? (float)dcy * CELL_F + ysh : 3.0e17f;
+                }
+            };
             int count = n;   // entries the rounds go through: all fish (direct) or the queue's survivors
             if (!direct) {
                 int qn = 0;
                 __syncwarp();
                 for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool keep = false;
-                    if (j < n) {
-                        const float2 q = *reinterpret_cast<const float2*>(&s_rec[j]);
-                        int dcx, dcy;
-                        if (image(s_c1[j].w, cxf, cyf, dcx, dcy)) {
-                            const float dx = (q.x + (float)dcx * CELL_F) - F.x, dy = (q.y + ((float)dcy * CELL_F + ysh)) - fyf;
-                            keep = fmaf(dx, dx, dy * dy) < (CELL_F + 2.f * BAND_R) * (CELL_F + 2.f * BAND_R);
-                        }
-                    }
+                    const int j = min(j0 + lane, n - 1);
+                    const float2 q = *reinterpret_cast<const float2*>(&s_rec[j]);
+                    float sx, sy;
+                    shift_of(s_c1[j].w, sx, sy);
+                    const float dx = (q.x + sx) - F.x, dy = (q.y + sy) - fyf;
+                    const bool keep = j0 + lane < n && fmaf(dx, dx, dy * dy) < (CELL_F + 2.f * BAND_R) * (CELL_F + 2.f * BAND_R);
                     const unsigned m = __ballot_sync(FULL, keep);
                     if (keep) s_queue[qn + __popc(m & lt_mask)] = (unsigned short)j;
                     qn += __popc(m);
@@ -130,22 +151,25 @@ __global__ void __launch_bounds__(ENS_THREADS, 4) ensemble_kernel(const Ensemble
             }
             PairAccR P;
             pair_acc_clear(P);
-            // pass 0: the branch-free round (pair_fast); a borderline pair, a tie or an exotic heading anywhere (rare) discards
-            // the sums and pass 1 redoes the fish with the generic per-lane code.  A lane without a pair gets a candidate beyond
-            // every radius (the round has no `live` predicate).
+            // pass 0: the branch-free round (pair_fast) on 32 entries at a time.  A lane beyond the last entry takes the focal
+            // fish itself: a pair with d2 == 0 fails every predicate (the reference's NaN drop), like a candidate whose shift is
+            // the far-away value.  A borderline pair, a tie or an exotic heading anywhere (rare) discards the sums and pass 1
+            // redoes the fish with the generic per-lane code.
             unsigned dirty = exotic ? 1u : 0u;
             for (int pass_no = exotic ? 1 : 0; pass_no < 2; ++pass_no) {
                 for (int q0 = 0; q0 < count; q0 += 32) {
                     const int e = q0 + lane;
                     const int jj = e < count ? (direct ? e : (int)s_queue[e]) : f;
                     const float4 Q = s_rec[jj];
-                    int dcx, dcy;
-                    const bool live = image(s_c1[jj].w, cxf, cyf, dcx, dcy) && e < count;
-                    if (direct && !__any_sync(FULL, live)) continue;
-                    const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
+                    const int cj = s_c1[jj].w;
                     if (pass_no == 0) {
-                        if (pair_fast<false>(F.x, fyf, F.z, F.w, qx, qy, Q.z, Q.w, P)) dirty = 1u;
+                        float sx, sy;
+                        shift_of(cj, sx, sy);
+                        if (pair_fast<false>(F.x, fyf, F.z, F.w, Q.x + sx, Q.y + sy, Q.z, Q.w, P)) dirty = 1u;
                     } else {
+                        int dcx, dcy;
+                        const bool live = image(cj, cxf, cyf, dcx, dcy) && e < count;
+                        const float qx = live ? Q.x + (float)dcx * CELL_F : 1.0e18f, qy = live ? Q.y + ((float)dcy * CELL_F + ysh) : 3.0e17f;
                         auto raw = [&](float& rx, float& ry, int& kcode, float&, float& fyr) { rx = Q.x; ry = Q.y; kcode = (dcy + 1) * 3 + (dcx + 1); fyr = F.y; };
                         auto ids = [&](uint32_t& my, uint32_t& nb) { my = (uint32_t)f; nb = (uint32_t)jj; };
                         pair_round_generic<false>(live, F.x, fyf, F.z, F.w, fdir, exotic, qx, qy, Q.z, Q.w, a.seed, replicate, step_move, raw, ids, P);
