@@ -330,7 +330,7 @@ int neighbour_pass(fishabm_ctx* ctx, int active_lag_max, bool do_sample, uint32_
     a.model = ctx->model;
     a.work_counter = ctx->work_counter + ctx->wc_parity;            // the persistent kernel's two cell counters alternate:
     a.work_counter_next = ctx->work_counter + (ctx->wc_parity ^ 1);  // each launch clears the one the next launch uses
-    if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->stats_on) CK(cudaMemsetAsync(ctx->stats, 0, 8 * sizeof(unsigned long long), ctx->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed && ctx->nb_events_used >= 4096) timed = false;  // per-launch timing covers the first 4096 passes of a call
     if (timed) {
@@ -1759,11 +1759,16 @@ int fishabm_enable_stats(fishabm_ctx* ctx, int32_t on) {
 
 int fishabm_last_pass_stats(fishabm_ctx* ctx, fishabm_pass_stats* out) {
     if (!ctx || !out) return FISHABM_E_ARG;
-    unsigned long long v[4] = {0, 0, 0, 0};
+    unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaSetDevice(ctx->p.device));
     CK(cudaMemcpyAsync(v, ctx->stats, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out->focal = v[0]; out->candidates = v[1]; out->interacting = v[2]; out->rechecked = v[3];
+    if (getenv("FISHABM_TAIL_DEBUG") && v[7]) {   // developer aid: how much of the neighbour launch its warps spent waiting for the last one
+        const double span = (double)(v[4] - ~v[6]), busy = (double)v[5] / (double)v[7];
+        fprintf(stderr, "fishabm: neighbour launch %.1f us from first warp start to last warp exit, mean warp busy %.1f us (%.1f %% idle), %llu warps\n",
+                span * 1e-3, busy * 1e-3, 100.0 * (1.0 - busy / span), v[7]);
+    }
     return 0;
 }
 

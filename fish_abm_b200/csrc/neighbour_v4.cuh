@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
     const unsigned lt_mask = (1u << lane) - 1u;
     V4WarpSmem& S = reinterpret_cast<V4WarpSmem*>(v4_smem_raw)[warp];
 
-    unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0;
+    unsigned long long st_cand = 0, st_inter = 0, st_rechk = 0, st_focal = 0, st_t0 = 0;
+    if (STATS) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t0));
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.work_counter_next = 0;
     const int ny = a.g.ny;
     const int col0 = a.g.own_c0 / ny, ncols = (a.g.own_c1 - a.g.own_c0) / ny;
@@ -382,6 +383,11 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
     if (STATS && a.stats && lane == 0) {
         atomicAdd(&a.stats[0], st_focal); atomicAdd(&a.stats[1], st_cand);
         atomicAdd(&a.stats[2], st_inter); atomicAdd(&a.stats[3], st_rechk);
+        // how evenly the dispenser kept the warps busy (FISHABM_TAIL_DEBUG prints it): last exit, summed busy time, earliest
+        // start (as a maximum of the complement), warps
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicMax(&a.stats[4], t1); atomicAdd(&a.stats[5], t1 - st_t0); atomicMax(&a.stats[6], ~st_t0); atomicAdd(&a.stats[7], 1ull);
     }
 }
 

@@ -61,6 +61,22 @@ def test_non_square_world(q100, w, h):
         step_against_oracle(S, d, w, h, q, 70, 3)
 
 
+@pytest.mark.parametrize("w,h,n", [(600, 600, 150), (1000, 800, 330), (600, 1400, 300)])
+def test_cell_pair_windows_in_tiny_worlds(q100, monkeypatch, w, h, n):
+    """the default neighbour kernel's work item is a vertical pair of cells with one 3 x 4 window; in a world of three or
+    four cell rows the window's rows wrap onto each other (a cell appears twice, as two periodic images), and with an odd
+    row count the last cell of a column is a single.  Forced here (a school this small would otherwise be split cell by
+    cell over the warps) and checked against the oracle step by step."""
+    monkeypatch.setenv("FISHABM_SPLIT", "1")
+    monkeypatch.setenv("FISHABM_PAIR_TAIL", "0")
+    d = state_wh(n, w, h, 67, speed=9.0)
+    q = synth.tile_quality(q100, w, h)
+    with School(n=n, w=w, h=h, seed=71) as S:
+        S.set_state(**d)
+        S.set_quality(q)
+        step_against_oracle(S, d, w, h, q, 71, 4)
+
+
 def test_non_square_world_slabs_and_ensemble_equal_whole_school(q100):
     w, h, n, steps = 2800, 1000, 5000, 12
     d = state_wh(n, w, h, 62, speed=11.0)
