@@ -404,6 +404,8 @@ def test_update_fused_into_the_neighbour_kernel_is_bit_identical(q100, monkeypat
     d = synth.uniform_state(n, w, w, seed=141)
     q = synth.tile_quality(q100, w, w)
     res = []
+    monkeypatch.setenv("FISHABM_NEIGHBOUR", "v3")   # the fused update exists in the one-window-per-cell design only ...
+    monkeypatch.setenv("FISHABM_SPLIT", "1")        # ... and only when a warp owns whole cells (a school this small would be split)
     for fused, slab in (("0", False), ("1", False), ("1", True)):
         monkeypatch.setenv("FISHABM_FUSED_UPDATE", fused)
         with School(n=n, w=w, h=w, seed=23, force_slab=slab) as S:
