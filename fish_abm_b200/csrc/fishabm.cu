@@ -557,6 +557,8 @@ int check_device_errors(fishabm_ctx* ctx) {
         ctx->have_state = false;
         CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), ctx->stream));
         if (bad & 1) return fail(ctx, FISHABM_E_ARG, "set_state: coordinates must be finite and inside [0,w] x [0,h]");
+        if (bad & 8) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: an id is outside [0, %d)", ctx->n);
+        if (bad & 16) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: a speed is too large: slabs need 3*speed < 200");
         if (bad & 4) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: a fish lies outside this slab's columns [%d, %d)", ctx->col0, ctx->col0 + ctx->own);
         return fail(ctx, FISHABM_E_NOMEM, "set_state: this slab holds more than its capacity of %d entries: raise fishabm_params.capacity", ctx->cap);
     }
@@ -909,7 +911,9 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     const size_t n = (size_t)ctx->n * ctx->R;
     cudaStream_t s = ctx->stream;
     if (ctx->slab) {  // a fish may not outrun its halo: |step| = speed * speed_factor <= 3 * speed must stay below one cell
-        for (size_t i = 0; i < n; ++i)
+        int bad_speed = 0;
+        for (size_t i = 0; i < n; ++i) bad_speed |= !(speed[i] * 3.0 < (double)CELL_I);
+        for (size_t i = 0; bad_speed && i < n; ++i)
             if (!(speed[i] * 3.0 < (double)CELL_I)) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state: speed %g of fish %zu: slabs need 3*speed < 200", speed[i], i);
     }
     CK(cudaMemcpyAsync(ctx->st_coords, coords, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -940,7 +944,7 @@ int fishabm_set_state(fishabm_ctx* ctx, const double* coords, const double* dir,
     const Buffers& b = ctx->buf[ctx->cur];
     IngestArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake,
                  b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted, nullptr,
-                 ctx->n, ctx->cap, ctx->g, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+                 ctx->n, ctx->cap, ctx->g, ctx->n, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
     ingest_kernel<<<cdiv(ctx->n, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     int rc = rebuild(ctx);
@@ -965,14 +969,10 @@ int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids,
     CK(cudaSetDevice(ctx->p.device));
     if (ctx->have_state) { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     ctx->pending_sample = false;
-    for (int i = 0; i < count; ++i) {
-        if (!(speed[i] * 3.0 < (double)CELL_I)) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: speed %g: slabs need 3*speed < 200", speed[i]);
-        // ids index pos_of_id[] on the device and the caller's arrays in fetch(): reject anything outside the school here
-        if (ids[i] < 0 || ids[i] >= ctx->n) return fail(ctx, FISHABM_E_ARG, "fishabm_set_state_owned: ids[%d] = %d is outside [0, %d)", i, ids[i], ctx->n);
-    }
     const size_t n = (size_t)count;
     cudaStream_t s = ctx->stream;
     { int rcb = begin_timed(ctx); if (rcb) return rcb; }
+    // the uploads go to staging arrays; the state itself is only touched by the ingest kernel below
     CK(cudaMemcpyAsync(ctx->st_coords, coords, 2 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_dir, dir, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_speed, speed, n * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -981,6 +981,8 @@ int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids,
     CK(cudaMemcpyAsync(ctx->st_rate, sample_rate, n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_intake, food_intake, n * sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->st_ids, ids, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    // ids and speeds are validated by the ingest kernel (it reads them anyway; a host-side pass over the 8.4M fish of a 2-GPU
+    // rank cost 10 ms in front of a 9 ms upload) and reported by fishabm_wait like every other bad input
     CK(cudaMemsetAsync(ctx->bad, 0, sizeof(int), s));
     CK(cudaMemsetAsync(ctx->err, 0, sizeof(int), s));
     CK(cudaMemsetAsync(ctx->cell_count, 0, ((size_t)ctx->ncell + 1) * sizeof(int), s));
@@ -989,7 +991,7 @@ int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids,
         const Buffers& b = ctx->buf[ctx->cur];
         IngestArgs a{ctx->st_coords, ctx->st_dir, ctx->st_speed, ctx->st_sf, ctx->st_lag, ctx->st_rate, ctx->st_intake,
                      b.rec, b.cold0, b.cold1, ctx->next_cell, ctx->next_rank, ctx->cell_count, ctx->n_unsorted, ctx->st_ids,
-                     count, ctx->cap, ctx->g, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
+                     count, ctx->cap, ctx->g, ctx->n, ctx->bad, (double)ctx->p.w, (double)ctx->p.h};
         if (count > 0) ingest_kernel<<<cdiv(count, 256), 256, 0, s>>>(a);
         ctx->launches += 1;
         int rc = rebuild(ctx);
@@ -1018,12 +1020,35 @@ int fishabm_get_state_owned(fishabm_ctx* ctx, int32_t* count, int32_t* ids, doub
     if (!count) return fail(ctx, FISHABM_E_ARG, "fishabm_get_state_owned: null count");
     if (ctx->ens) return fail(ctx, FISHABM_E_STATE, "fishabm_get_state_owned is for single schools / slabs");
     CK(cudaSetDevice(ctx->p.device));
-    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
-    int cnt = 0;
+    int cnt = 0;   // (a pending sample() moves no fish: the owned range and the sorted order are already final)
     if ((rc = owned_range(ctx, &cnt))) return rc;
     if (cnt > *count) { const int have = *count; *count = cnt; return fail(ctx, FISHABM_E_NOMEM, "fishabm_get_state_owned: %d fish owned, arrays hold %d", cnt, have); }
     *count = cnt;
     cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)cnt;
+    // as in fishabm_get_state: what a pending sample() cannot change (ids, positions, headings, speeds: 36 of 56 bytes per fish)
+    // is exported first and goes to the host on the second stream while the pending pass runs
+    const bool early = ctx->pending_sample && cnt > 0 && (ids || coords || dir || speed);
+    if (early) {
+        const Buffers& b0 = ctx->buf[ctx->cur];
+        ExportArgs e{b0.rec, b0.cold0, b0.cold1, b0.cell, ctx->cell_start, coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr,
+                     speed ? ctx->st_speed : nullptr, nullptr, nullptr, nullptr, nullptr, ids ? ctx->st_ids : nullptr, ctx->g, 1};
+        export_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(e);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_copy, s));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+        if (ids) CK(cudaMemcpyAsync(ids, ctx->st_ids, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (speed) CK(cudaMemcpyAsync(speed, ctx->st_speed, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ids = nullptr; coords = nullptr; dir = nullptr; speed = nullptr;   // done: the second export leaves them out
+    }
+    struct CopyGuard {   // whatever happens below, the early downloads have landed before the call returns
+        fishabm_ctx* c; bool on;
+        ~CopyGuard() { if (on) cudaStreamSynchronize(c->copy_stream); }
+    } guard{ctx, early};
+    { int rcf = flush_pending(ctx); if (rcf) return rcf; }
     const Buffers& b = ctx->buf[ctx->cur];
     ExportArgs a{b.rec, b.cold0, b.cold1, b.cell, ctx->cell_start,
                  coords ? ctx->st_coords : nullptr, dir ? ctx->st_dir : nullptr, speed ? ctx->st_speed : nullptr,
@@ -1032,7 +1057,6 @@ int fishabm_get_state_owned(fishabm_ctx* ctx, int32_t* count, int32_t* ids, doub
     if (cnt > 0) export_kernel<<<cdiv(cnt, 256), 256, 0, s>>>(a);
     ctx->launches += 1;
     CK(cudaGetLastError());
-    const size_t n = (size_t)cnt;
     if (ids) CK(cudaMemcpyAsync(ids, ctx->st_ids, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (coords) CK(cudaMemcpyAsync(coords, ctx->st_coords, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dir) CK(cudaMemcpyAsync(dir, ctx->st_dir, n * sizeof(double), cudaMemcpyDeviceToHost, s));

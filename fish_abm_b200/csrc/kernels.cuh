@@ -1062,7 +1062,9 @@ struct IngestArgs {
     const int* ids;   // null: fish i has id i (whole-school arrays); else the arrays are this slab's own fish only
     int n_global, cap_total;
     Grid g;
-    int* bad;  // set to 1 if a coordinate is outside [0,W] x [0,H] or not finite, 2 if the arrays overflow
+    int n_school;      // fish in the whole school (slab-local input: ids are validated against it)
+    int* bad;  // bits: 1 a coordinate is outside [0,W] x [0,H] or not finite, 2 the arrays overflow, 4 a fish of a slab-local input
+               // lies outside the slab's columns, 8 one of its ids is outside [0, n_school), 16 its speed can outrun the halo
     double w, h;
 };
 
@@ -1092,6 +1094,12 @@ __global__ void ingest_kernel(const IngestArgs a) {
     float sn, cs;
     heading_vector(dirf, cs, sn);
     const int id = a.ids ? a.ids[i] : i;
+    if (a.ids) {   // slab-local input (fishabm_set_state_owned): validated here, while it is being read anyway, and reported by fishabm_wait
+        // ids index pos_of_id[] on the device and the caller's arrays on the host: an entry with an id outside the school is dropped
+        if ((unsigned)id >= (unsigned)a.n_school) { atomicOr(a.bad, 8); return; }
+        // a fish may not outrun its halo: |step| = speed * speed_factor <= 3 * speed must stay below one cell
+        if (!(a.speed[i] * 3.0 < (double)CELL_I)) atomicOr(a.bad, 16);
+    }
     const float4 r = make_float4(ox, oy, cs, sn);
     const float4 c0 = make_float4(dirf, (float)a.speed[i], (float)a.sf[i], 0.f);
     const int4 c1 = make_int4(a.lag[i], a.rate[i], a.intake[i], id);
@@ -1241,12 +1249,17 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ScatterArgs a) {
     }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(*a.n_unsorted, a.cap)) return;  // claims beyond the capacity were refused (and reported)
+    // the records are requested together with the keys (not behind the ghost test and the gather of the cell's start): the
+    // kernel is bound by memory latency, and this takes one round trip out of its dependency chain
     const int c = a.next_cell[i];
+    const int rank = a.next_rank[i];
+    const float4 r = a.rec_in[i], c0 = a.cold0_in[i];
+    const int4 c1 = a.cold1_in[i];
     if (c < 0) return;  // last step's ghost
-    const int dst = a.start[c] + a.next_rank[i];
-    a.rec_out[dst] = a.rec_in[i];
-    a.cold0_out[dst] = a.cold0_in[i];
-    a.cold1_out[dst] = a.cold1_in[i];
+    const int dst = a.start[c] + rank;
+    a.rec_out[dst] = r;
+    a.cold0_out[dst] = c0;
+    a.cold1_out[dst] = c1;
     a.cell_out[dst] = c;
 }
 

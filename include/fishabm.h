@@ -269,7 +269,8 @@ int fishabm_slab_attach(fishabm_ctx* ctx, const fishabm_slab_endpoint* left, con
  * fishabm_set_state_owned: `count` fish with global ids ids[], every one inside this slab's columns (x in
  * [col0*200, col1*200)); afterwards the slabs refresh each other's halo columns with one exchange.  Collective over
  * all ranks; the call only ENQUEUES (so that several slabs of one process can be driven in turn): follow it with
- * fishabm_wait, which also reports bad input.  fishabm_get_state_owned: the fish this slab owns now, compact, with
+ * fishabm_wait, which also reports bad input (coordinates outside the world or the slab's columns, ids outside [0, n),
+ * speeds with 3*speed >= 200: all checked on the device while the arrays are ingested).  fishabm_get_state_owned: the fish this slab owns now, compact, with
  * their ids; *count is the capacity of the arrays on entry and the number of fish on return. */
 int fishabm_set_state_owned(fishabm_ctx* ctx, int32_t count, const int32_t* ids, const double* coords, const double* dir,
                             const double* speed, const double* speed_factor, const int32_t* lag, const int32_t* sample_rate,
