@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
             // filter steps (64 candidates each) of the three window rows around each cell of the item (single batch): the first
             // cell sees rows 0..2 = slots [0, pre[9]) (= T for a single cell: lanes >= ncw hold no fish), the second rows 1..3 =
             // slots [pre[3], T).  (Shuffles, not shared-memory reads: the compiler keeps shuffled values in uniform registers.)
-            const int st_end0 = (__shfl_sync(FULL, pre, 9) + 63) >> 6;
-            const int st_beg1 = __shfl_sync(FULL, pre, 3) >> 6;
+            const int pre9 = __shfl_sync(FULL, pre, 9), pre3 = __shfl_sync(FULL, pre, 3);
+            const int st_end0 = (pre9 + 63) >> 6;
+            const int st_beg1 = pre3 >> 6;
             const int st_end1 = (T + 63) >> 6;
             __syncwarp();
             // y frame: window row ky holds cell row cy0 - 1 + ky; the frame's zero is the odd row of the pair
@@ -289,7 +290,9 @@ __global__ void __launch_bounds__(V4_THREADS, 4) neighbour_kernel_v4(const Neigh
                         }
                         S.queue[qn + lane] = (unsigned char)(V4_SLOTS - 1);   // pad the last round with the far-away slot
                         __syncwarp();
-                        if (STATS) st_cand += (unsigned)fill;
+                        // candidates in SURVEY's sense: the fish of the 3 x 3 cells around the focal fish's own cell (not the
+                        // whole pair window)
+                        if (STATS) st_cand += (unsigned)(nbatch > 1 ? fill : (part ? T - pre3 : pre9));
                         // ---- pair rounds (compacted pairs, one per lane, same focal fish in every lane)
                         const float4 F = S.frec[f];  // broadcast
                         PairAccR P;
