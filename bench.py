@@ -396,7 +396,9 @@ def ours(args, rank: int, world: int, local_rank: int):
         slots = sm_count * 4 * peaks.get("sm_max_mhz", 1965.0) * 1e6 * per_launch_ms * 1e-3
         issue = {"ncu_issue_active_pct": cap.get("issue_active_pct"), "warp_instructions_per_focal_fish": cap["warp_instructions"] / cap["focal_per_launch"],
                  "estimated_frac_timed_launches": cap["warp_instructions"] / cap["focal_per_launch"] * focal / slots,
-                 "how": "ncu: smsp__issue_active of the captured launch; estimate: (capture's warp instructions / its focal fish) x live focal fish / (SMs x 4 x sm_max_mhz x launch time)"}
+                 "how": "ncu: smsp__issue_active of the captured launch (the measured figure); estimate: (capture's warp instructions / its focal fish) x live "
+                        "focal fish / (SMs x 4 x sm_max_mhz x launch time) -- an UPPER estimate: the per-cell work is spread over more focal fish in the "
+                        "timed launches than in the captured one"}
     roofline = {"bound": "fp32", "kernel": kname.rstrip("<"), "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp32_peak, "traffic": cap["dram_bytes"] if cap else None,
                 "traffic_note": "ncu dram__bytes_read+write of one launch (the 1M-fish state is L2-resident: 16 B x 1M hot records)" if cap else None,
