@@ -113,7 +113,9 @@ struct fishabm_ctx {
     uint8_t* quality = nullptr;
     int *upd_count = nullptr, *upd_idx = nullptr;  // upd_count[2]: alternate by sample(), each apply clears the other
     int upd_parity = 0, wc_parity = 0;
-    int* scan_sync = nullptr;   // [2] ticket + epoch flag of the fused scan
+    int* scan_sync = nullptr;   // [2] ticket + epoch flag of the fused scan, [1] ticket of the chained scan
+    unsigned long long* scan_desc = nullptr;   // chained scan: one published word per tile
+    bool scan_chained = true;   // FISHABM_SCAN=coop: the cooperative one-launch scan instead (A/B)
     int scan_epoch = 0, scan_resident = 0;
     uint8_t* upd_val = nullptr;
     unsigned long long* stats = nullptr;  // 4 pass counters + 1 scratch for sums
@@ -169,7 +171,8 @@ Model to_device_model(const fishabm_model_params& m) {
     Model d;
     d.lag_after_feed = m.lag_after_feed; d.rate_fed = m.sample_rate_fed; d.rate_unfed = m.sample_rate_unfed;
     d.sample_draw_max = m.sample_draw_max; d.error_range = m.error_range; d.randomwalk_range = m.randomwalk_range;
-    d.alone_align_min = m.alone_align_min; d.pad = 0;
+    d.alone_align_min = m.alone_align_min;
+    { const uint32_t range = 2u * (uint32_t)m.error_range + 1u; d.error_reject = (0u - range) % range; }
     d.fed_sf = (float)m.fed_speed_factor; d.w_align = (float)m.weight_align; d.w_attract = (float)m.weight_attract; d.pad2 = 0.f;
     return d;
 }
@@ -232,7 +235,7 @@ cudaError_t preload_kernels() {
     L((const void*)neighbour_kernel_v4<false>); L((const void*)neighbour_kernel_v4<true>); L((const void*)scan_finish_kernel);
     L((const void*)neighbour_kernel_v3<false, false>); L((const void*)neighbour_kernel_v3<true, false>);
     L((const void*)neighbour_kernel_v3<false, true>); L((const void*)neighbour_kernel_v3<true, true>);
-    L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
+    L((const void*)scan_chained_kernel); L((const void*)scan_fused_kernel); L((const void*)scan_tile_offsets_kernel); L((const void*)scan_tile_sums_kernel);
     L((const void*)scatter_kernel); L((const void*)slab_publish_kernel); L((const void*)slab_wait_kernel);
     L((const void*)sum_quality_kernel); L((const void*)update_kernel); L((const void*)check_fp64_kernel); L((const void*)brute_fp64_pass_kernel);
     return e;
@@ -258,7 +261,14 @@ int rebuild(fishabm_ctx* ctx) {
     NvtxRange nv("fishabm: K2 scan + K3 scatter (counting sort)");
     const int ntiles = cdiv(ctx->ncell, SCAN_TILE);
     bool fused_scan = false;
-    if (ntiles <= ctx->scan_resident) {
+    if (ctx->scan_chained) {
+        ctx->scan_epoch = (ctx->scan_epoch + 1) & 0x3FFFFFFF;
+        if (ctx->scan_epoch == 0) ctx->scan_epoch = 1;   // (0 is what the words are cleared to)
+        ScanChainArgs f{ctx->cell_count, ctx->ncell, ctx->cell_start, ctx->scan_desc, ctx->scan_sync + 2, (unsigned)ctx->scan_epoch, ntiles};
+        scan_chained_kernel<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(f);
+        fused_scan = true;
+        ctx->launches -= 2;
+    } else if (ntiles <= ctx->scan_resident) {
         // one launch: its blocks wait for the block that scans the tile sums, so they must all be resident at the same time.
         // A COOPERATIVE launch makes the driver guarantee that (whatever else shares the GPU) or refuse the launch.
         ScanFusedArgs f{ctx->cell_count, ctx->ncell, ctx->tile_sums, ctx->cell_start, ctx->scan_sync, ctx->scan_sync + 1, ctx->scan_epoch + 1, ntiles};
@@ -807,13 +817,14 @@ int fishabm_create(const fishabm_params* p, fishabm_ctx** out) {
     A(dalloc(&c->quality, nq));
     A(dalloc(&c->upd_count, 2)); A(dalloc(&c->upd_idx, cap)); A(dalloc(&c->upd_val, cap));
     A(dalloc(&c->stats, 8)); A(dalloc(&c->work_counter, 2)); A(dalloc(&c->bad, 1)); A(dalloc(&c->pos_of_id, n));
-    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R)); A(dalloc(&c->scan_sync, 2));
+    A(dalloc(&c->n_unsorted, 1)); A(dalloc(&c->err, 1)); A(dalloc(&c->d_sums, (size_t)c->R)); A(dalloc(&c->scan_sync, 4)); A(dalloc(&c->scan_desc, (size_t)cdiv(c->ncell, SCAN_TILE) + 1));
     A(dalloc(&c->d_models, (size_t)c->R));
     if (ok) {
         std::vector<Model> hm((size_t)c->R, c->model);
         A(cudaMemcpy(c->d_models, hm.data(), hm.size() * sizeof(Model), cudaMemcpyHostToDevice));
     }
-    if (ok) A(cudaMemset(c->scan_sync, 0, 2 * sizeof(int)));
+    if (ok) { A(cudaMemset(c->scan_sync, 0, 4 * sizeof(int))); A(cudaMemset(c->scan_desc, 0, ((size_t)cdiv(c->ncell, SCAN_TILE) + 1) * sizeof(unsigned long long))); }
+    if (const char* sc = getenv("FISHABM_SCAN")) c->scan_chained = strcmp(sc, "coop") != 0;
     A(dalloc(&c->st_coords, 2 * n)); A(dalloc(&c->st_dir, n)); A(dalloc(&c->st_speed, n)); A(dalloc(&c->st_sf, n));
     A(dalloc(&c->st_lag, n)); A(dalloc(&c->st_rate, n)); A(dalloc(&c->st_intake, n)); A(dalloc(&c->st_i4, 4 * n)); A(dalloc(&c->st_ids, n));
     if (c->slab) {
@@ -885,7 +896,7 @@ void fishabm_destroy(fishabm_ctx* c) {
     cudaFree(c->next_cell); cudaFree(c->next_rank); cudaFree(c->cell_count); cudaFree(c->cell_start); cudaFree(c->tile_sums);
     cudaFree(c->cnt); cudaFree(c->turn); cudaFree(c->aux); cudaFree(c->quality);
     cudaFree(c->upd_count); cudaFree(c->upd_idx); cudaFree(c->upd_val); cudaFree(c->stats); cudaFree(c->work_counter); cudaFree(c->bad); cudaFree(c->pos_of_id);
-    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums); cudaFree(c->scan_sync); cudaFree(c->d_models);
+    cudaFree(c->n_unsorted); cudaFree(c->err); cudaFree(c->d_sums); cudaFree(c->scan_sync); cudaFree(c->scan_desc); cudaFree(c->d_models);
     cudaFree(c->st_coords); cudaFree(c->st_dir); cudaFree(c->st_speed); cudaFree(c->st_sf);
     cudaFree(c->st_lag); cudaFree(c->st_rate); cudaFree(c->st_intake); cudaFree(c->st_i4); cudaFree(c->st_ids);
     cudaFree(c->out_left); cudaFree(c->out_right); cudaFree(c->in_left); cudaFree(c->in_right);

@@ -70,7 +70,7 @@ struct Model {
     int error_range;         // 10,  :29  distrib_error(-10, 10)
     int randomwalk_range;    // 45,  :30  distrib_randomwalk(-45, 45)
     int alone_align_min;     // 5,   :546 alone = no avoid-zone neighbour and fewer than 5 align-zone neighbours
-    int pad;
+    uint32_t error_reject;   // 2^32 mod (2 * error_range + 1): the rejection threshold of the error draw (philox.cuh: draw_known)
     float fed_sf;            // 0.5, :566
     float w_align;           // 1.7, :385-386 (1.7 - i, i = 0)
     float w_attract;         // 0.7  (1.7 - i, i = 1)
@@ -903,7 +903,8 @@ __device__ __forceinline__ void update_fish(const UpdateArgs& a, const int i, co
     }
 
     if (a.do_move) {  // move(), fish_mod.cpp:165-179
-        const int err = fishrng::draw(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -a.model.error_range, a.model.error_range);
+        const int err = fishrng::draw_known(a.seed, a.replicate, a.step_move, (uint32_t)c1.w, STREAM_ERROR, 0, -a.model.error_range,
+                                            2u * (uint32_t)a.model.error_range + 1u, a.model.error_reject);
         float4 r = a.rec[i];
         int cx = cx0, cy = cy0;
         const bool moving = c1.x == 0;
@@ -1226,6 +1227,56 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_fused_kernel(const ScanFuse
     }
     __syncthreads();
     int run = ex + *reinterpret_cast<volatile int*>(&a.tile_sums[blockIdx.x]);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < a.n) { a.start[base + k] = run; run += vals[k]; a.count[base + k] = 0; }
+    if (base <= a.n - 1 && a.n - 1 < base + SCAN_ITEMS) a.start[a.n] = run;
+}
+
+// The same scan as ONE ordinary launch that needs no co-residency (default): a chained scan with decoupled look-back.  A block
+// takes its tile number from a ticket counter, so a tile only ever waits for tiles whose blocks are already running; it
+// publishes its tile sum, then a warp looks back over the published words of the preceding tiles -- 32 at a time, summing
+// tile sums until it meets a tile that already knows its inclusive prefix -- and publishes its own prefix.  A word carries
+// (epoch << 2 | state) in its high half and the value in its low half, written and read as one 64-bit access; the epoch makes
+// last step's words invalid without a reset.
+struct ScanChainArgs { int* count; int n; int* start; unsigned long long* desc; int* ticket; unsigned epoch; int ntiles; };
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chained_kernel(const ScanChainArgs a) {
+    __shared__ int s_warp[33];
+    __shared__ int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int vals[SCAN_ITEMS];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { vals[k] = (base + k < a.n) ? a.count[base + k] : 0; v += vals[k]; }
+    int total;
+    const int ex = block_exclusive_scan(v, &total, s_warp);
+    const unsigned long long tag_sum = (unsigned long long)((a.epoch << 2) | 1u) << 32, tag_prefix = (unsigned long long)((a.epoch << 2) | 2u) << 32;
+    volatile unsigned long long* desc = a.desc;
+    if (threadIdx.x == 0) {
+        desc[tile] = (tile == 0 ? tag_prefix : tag_sum) | (unsigned)total;
+        if (tile == 0) s_prefix = 0;
+        if (tile == a.ntiles - 1) *a.ticket = 0;   // every ticket of this launch has been taken: ready for the next one
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int prefix = 0;
+        for (int look = tile - 1;; look -= 32) {
+            const int idx = look - lane;
+            unsigned long long d = 0;
+            if (idx >= 0) do { d = desc[idx]; } while ((unsigned)(d >> 34) != a.epoch);   // published in THIS scan
+            const bool is_prefix = idx >= 0 && ((unsigned)(d >> 32) & 3u) == 2u;
+            const unsigned pm = __ballot_sync(0xFFFFFFFFu, is_prefix);
+            const int first = pm ? __ffs((int)pm) - 1 : 31;   // tiles up to the nearest one with a known prefix count
+            prefix += __reduce_add_sync(0xFFFFFFFFu, (idx >= 0 && lane <= first) ? (int)(unsigned)d : 0);
+            if (pm) break;   // (tile 0 always publishes a prefix: the walk ends there at the latest)
+        }
+        if (lane == 0) { s_prefix = prefix; desc[tile] = tag_prefix | (unsigned)(prefix + total); }
+    }
+    __syncthreads();
+    int run = ex + s_prefix;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k)
         if (base + k < a.n) { a.start[base + k] = run; run += vals[k]; a.count[base + k] = 0; }

@@ -50,12 +50,22 @@ FISH_HD uint32_t word(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t
 // integer in [a,b]; consumes words k0, k0+1, ... until one passes the rejection test
 FISH_HD int draw(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t id, uint32_t stream, uint32_t k0, int a, int b) {
     const uint32_t range = (uint32_t)(b - a) + 1u;
+    const uint32_t reject_below = (0u - range) % range;
     for (uint32_t k = k0;; ++k) {
         const uint32_t u = word(seed, replicate, step, id, stream, k);
         const uint32_t lo = u * range;
-        // accepted unless lo < 2^32 mod range (< range): the modulo -- an integer division on the device -- is only worked out
-        // for the one word in 2^32 / range that gets that far, as libstdc++ itself does
-        if (lo >= range || lo >= (0u - range) % range) return a + (int)mulhi32(u, range);
+        if (lo >= reject_below) return a + (int)mulhi32(u, range);
+    }
+}
+
+// the same draw for a range whose rejection threshold 2^32 mod range is already known (the per-fish update: the model's
+// error range is a launch constant; the modulo is an integer division on the device)
+FISH_HD int draw_known(uint64_t seed, uint32_t replicate, uint32_t step, uint32_t id, uint32_t stream, uint32_t k0, int a, uint32_t range,
+                       uint32_t reject_below) {
+    for (uint32_t k = k0;; ++k) {
+        const uint32_t u = word(seed, replicate, step, id, stream, k);
+        const uint32_t lo = u * range;
+        if (lo >= reject_below) return a + (int)mulhi32(u, range);
     }
 }
 
