@@ -395,7 +395,7 @@ __device__ __forceinline__ bool pair_math(bool live, float fx, float fy, float f
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Round form of the pair math (neighbour_kernel_v3, ensemble_kernel): 32 pairs of ONE focal fish, one per lane.
+// Round form of the pair math (neighbour_kernel_v3; the ensemble kernel and neighbour_kernel_v4 use pair_fast below): 32 pairs of ONE focal fish, one per lane.
 // The hot path is straight-line, branch-free code: geometry, rounding bands, classification, bearing, weight, sincos.
 // Everything rare -- a borderline predicate (fp64 re-check), a tie draw -- is detected as a flag and, if ANY lane of
 // the round raises it (about 1 round in 2500), the whole round is redone by the generic pair_math above before

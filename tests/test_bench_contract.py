@@ -27,5 +27,5 @@ def test_roofline_helpers():
     assert bench.flops_alg(10, 2) == 13 * 10 + 20 * 2
     peaks, how = bench.measured_peaks()
     assert peaks["hbm_gbs"] > 1000 and how in ("measured", "fallback")
-    cap = bench.ncu_capture("neighbour_kernel_v2")
+    cap = bench.ncu_capture("neighbour_kernel_v4")
     assert cap is None or (cap["dram_bytes"] > 0 and 0 < cap["issue_active_pct"] <= 100)

@@ -9,7 +9,7 @@ from test_gpu_parity import as_dict, to32
 g = np.load("tests/golden/golden_ref.npz"); q100 = load_quality_csv("tests/golden/quality.csv")
 case = sys.argv[1] if len(sys.argv) > 1 else "E"
 st = golden_state(g, f"{case}_in")
-for variant in ("v1", "v2"):
+for variant in ("v1", "v3", "v4"):
     os.environ["FISHABM_NEIGHBOUR"] = variant
     S = School(n=st.n, seed=int(g["seed"])); S.set_state(**as_dict(st)); S.set_quality(q100); S.step_index = int(g[f"{case}_step"])
     O = Oracle(to32(st), 2000, 2000, q100.copy(), seed=int(g["seed"]))

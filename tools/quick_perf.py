@@ -1,5 +1,5 @@
 """Quick A/B timing of the neighbour kernel at the benchmark state (C3 by default): ms per fused step and per neighbour launch.
-usage: [FISHABM_LIB=...] [FISHABM_NEIGHBOUR=v2] python tools/quick_perf.py [n_fish]"""
+usage: [FISHABM_LIB=...] [FISHABM_NEIGHBOUR=v3] python tools/quick_perf.py [n_fish]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
